@@ -1,0 +1,103 @@
+"""ctypes bindings for oracle/_ref/libgm_ref_<app>.so -- TEST INFRASTRUCTURE ONLY.
+
+The libraries are the UNMODIFIED reference (narayanan2004/GraphMat) compiled
+single-rank by oracle/Makefile from /root/reference; see oracle/ref_driver.cpp.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_libs = {}
+
+
+def available(app="pagerank"):
+    return os.path.exists(os.path.join(_HERE, "_ref", "libgm_ref_%s.so" % app))
+
+
+def _lib(app):
+    if app not in _libs:
+        path = os.path.join(_HERE, "_ref", "libgm_ref_%s.so" % app)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
+        _libs[app] = C.CDLL(path)
+    return _libs[app]
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def max_threads():
+    return _lib("pagerank").gm_ref_max_threads()
+
+
+def pagerank(n, src, dst, val=None, threads=4, iterations=-1):
+    """-> (pagerank f32[n], degree i32[n], iterations, ms)."""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    pr = np.empty(n, np.float32)
+    deg = np.empty(n, np.int32)
+    ms = C.c_double()
+    it = _lib("pagerank").gm_ref_pagerank(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src),
+                                          _p(dst), _p(val), C.c_int(iterations), _p(pr), _p(deg), C.byref(ms))
+    return pr, deg, it, ms.value
+
+
+def bfs(n, src, dst, source, val=None, threads=4):
+    """-> (depth u32[n], parent u64[n], iterations, reachable, ms)."""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    depth = np.empty(n, np.uint32)
+    parent = np.empty(n, np.uint64)
+    ms = C.c_double()
+    reach = C.c_int()
+    it = _lib("bfs").gm_ref_bfs(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst),
+                                _p(val), C.c_int(source), _p(depth), _p(parent), C.byref(reach), C.byref(ms))
+    return depth, parent, it, reach.value, ms.value
+
+
+def sssp(n, src, dst, val, source, threads=4):
+    """-> (distance u32[n], iterations, reachable, ms)."""
+    src, dst, val = _i32(src), _i32(dst), _i32(val)
+    dist = np.empty(n, np.uint32)
+    ms = C.c_double()
+    reach = C.c_int()
+    it = _lib("sssp").gm_ref_sssp(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst),
+                                  _p(val), C.c_int(source), _p(dist), C.byref(reach), C.byref(ms))
+    return dist, it, reach.value, ms.value
+
+
+def deltastepping(n, src, dst, val, delta, source, threads=4):
+    """-> (distance u32[n], bucket i32[n], buckets_processed, reachable, ms)."""
+    src, dst, val = _i32(src), _i32(dst), _i32(val)
+    dist = np.empty(n, np.uint32)
+    bucket = np.empty(n, np.int32)
+    ms = C.c_double()
+    reach = C.c_int()
+    nb = _lib("deltastepping").gm_ref_deltastepping(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)),
+                                                    _p(src), _p(dst), _p(val), C.c_int(delta), C.c_int(source),
+                                                    _p(dist), _p(bucket), C.byref(reach), C.byref(ms))
+    return dist, bucket, nb, reach.value, ms.value
+
+
+def sgd(m, n, src, dst, val, K=20, iterations=10, lam=0.001, step=0.00000035, threads=4):
+    """-> (lv f64[max(m,n),K], rmse_before, rmse_after, ms)."""
+    src, dst, val = _i32(src), _i32(dst), _i32(val)
+    nv = max(m, n)
+    lv = np.empty((nv, K), np.float64)
+    rmse = np.empty(2, np.float64)
+    ms = C.c_double()
+    r = _lib("sgd").gm_ref_sgd(C.c_int(threads), C.c_int(K), C.c_int(m), C.c_int(n), C.c_int(len(src)), _p(src),
+                               _p(dst), _p(val), C.c_int(iterations), C.c_double(lam), C.c_double(step), _p(lv),
+                               _p(rmse), C.byref(ms))
+    if r < 0:
+        raise ValueError("reference SGD built for K in {4, 20, 32}")
+    return lv, rmse[0], rmse[1], ms.value

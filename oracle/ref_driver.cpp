@@ -1,0 +1,317 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Builds the UNMODIFIED reference (headers under /root/reference/include and the
+// vertex programs in /root/reference/src/<App>.cpp, included from where they lie,
+// never copied) as a single-rank shared library, against the stub <mpi.h> and
+// Boost headers in oracle/stubs/.  One .so per app (the app sources define
+// clashing globals such as MAX_DIST), selected with -DGM_REF_APP_<NAME>.
+//
+// Each entry point restates the few driver lines of the app's run_* function
+// (cited below) but takes the edge list from memory instead of a file and
+// returns the FULL vertex-property arrays (the apps print only the first 10-25
+// vertices).  Edge ids are public, 1-based, exactly what load_edgelist
+// (/root/reference/include/GMDP/utils/edgelist.h:242-334) would deliver.
+//
+// Used for: (1) pinning oracle/gm_oracle.c, (2) generating tests/golden/*,
+// (3) the CPU baseline of bench.py (`cpu_baseline.kind == "reference"`).
+#include <omp.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <sys/time.h>
+#include <cstdio>
+#include <cstdlib>
+
+#define main gm_ref_app_main  // keep the app's own main() out of the way
+#if defined(GM_REF_APP_PAGERANK)
+#include "src/PageRank.cpp"
+#elif defined(GM_REF_APP_BFS)
+#include "src/BFS.cpp"
+#elif defined(GM_REF_APP_SSSP)
+#include "src/SSSP.cpp"
+#elif defined(GM_REF_APP_DELTASTEPPING)
+#include "src/DeltaStepping.cpp"
+#elif defined(GM_REF_APP_SGD)
+#include "src/SGD.cpp"
+#else
+#error "pick one reference app"
+#endif
+#undef main
+
+namespace {
+
+// The reference prints per-tile diagnostics on stdout; silence unless asked.
+struct Quiet {
+  int saved;
+  Quiet() : saved(-1) {
+    if (getenv("GM_REF_VERBOSE")) return;
+    fflush(stdout);
+    saved = dup(1);
+    int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1);
+    close(nul);
+  }
+  ~Quiet() {
+    if (saved < 0) return;
+    fflush(stdout);
+    std::cout.flush();
+    dup2(saved, 1);
+    close(saved);
+  }
+};
+
+double now_ms() {
+  struct timeval t;
+  gettimeofday(&t, 0);
+  return t.tv_sec * 1e3 + t.tv_usec * 1e-3;
+}
+
+// In-memory equivalent of Graph::ReadMTX (/root/reference/include/Graph.h:248-260):
+// edge list -> square -> ReadEdgelist.
+template <class G>
+void ingest(G& g, int m, int n, int nnz, const int* src, const int* dst, const int* val, bool square) {
+  GraphMat::edgelist_t<int> E(m, n, nnz);
+  for (int i = 0; i < nnz; i++) {
+    E.edges[i].src = src[i];
+    E.edges[i].dst = dst[i];
+    E.edges[i].val = val ? val[i] : 1;
+  }
+  if (square && E.m != E.n) {
+    int mx = std::max(E.m, E.n);
+    E.m = mx;
+    E.n = mx;
+  }
+  g.ReadEdgelist(E);
+  E.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gm_ref_max_threads() { return omp_get_max_threads(); }
+
+#if defined(GM_REF_APP_PAGERANK)
+// run_pagerank, /root/reference/src/PageRank.cpp:115-161.  `iterations` <= 0 means
+// UNTIL_CONVERGENCE (the app's setting); > 0 runs exactly that many (for fixed-count parity).
+struct CountingPageRank : public PageRank<int> {
+  int iters;
+  CountingPageRank() : iters(0) {}
+  void do_every_iteration(int it) { iters = it + 1; }
+};
+int gm_ref_pagerank(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val,
+                    int iterations, float* pagerank, int* degree, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<PR, int> G;
+  CountingPageRank pr;
+  Degree<PR, int> dg;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  auto dg_tmp = GraphMat::graph_program_init(dg, G);
+  G.setAllActive();
+  GraphMat::run_graph_program(&dg, G, 1, &dg_tmp);
+  GraphMat::graph_program_clear(dg_tmp);
+  auto pr_tmp = GraphMat::graph_program_init(pr, G);
+  double t0 = now_ms();
+  G.setAllActive();
+  GraphMat::run_graph_program(&pr, G, iterations > 0 ? iterations : GraphMat::UNTIL_CONVERGENCE, &pr_tmp);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(pr_tmp);
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    PR p = G.getVertexproperty(i);
+    pagerank[i - 1] = p.pagerank;
+    degree[i - 1] = p.degree;
+  }
+  return pr.iters;
+}
+#endif
+
+#if defined(GM_REF_APP_BFS)
+// run_bfs, /root/reference/src/BFS.cpp:110-156.
+struct CountingBFS : public BFS2 {
+  int iters;
+  CountingBFS() : iters(0) {}
+  void do_every_iteration(int it) {
+    BFS2::do_every_iteration(it);
+    iters = it + 1;
+  }
+};
+int gm_ref_bfs(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val, int source,
+               unsigned int* depth, unsigned long long* parent, int* reachable, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<BFSD2> G;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  for (int i = 0; i < G.getNumberOfVertices(); i++) {
+    BFSD2 vp = G.getVertexproperty(i + 1);
+    vp.id = i + 1;
+    G.setVertexproperty(i + 1, vp);
+  }
+  CountingBFS b;
+  auto b_tmp = GraphMat::graph_program_init(b, G);
+  G.setAllInactive();
+  auto s = G.getVertexproperty(source);
+  s.depth = 0;
+  G.setVertexproperty(source, s);
+  G.setActive(source);
+  double t0 = now_ms();
+  GraphMat::run_graph_program(&b, G, GraphMat::UNTIL_CONVERGENCE, &b_tmp);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(b_tmp);
+  int r = 0;
+  G.applyReduceAllVertices(&r, reachable_or_not);
+  if (reachable) *reachable = r;
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    BFSD2 p = G.getVertexproperty(i);
+    depth[i - 1] = p.depth;
+    parent[i - 1] = p.parent;
+  }
+  return b.iters;
+}
+#endif
+
+#if defined(GM_REF_APP_SSSP)
+// run_sssp, /root/reference/src/SSSP.cpp:102-142.
+struct CountingSSSP : public SSSP<int> {
+  int iters;
+  CountingSSSP() : iters(0) {}
+  void do_every_iteration(int it) { iters = it + 1; }
+};
+int gm_ref_sssp(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val, int source,
+                unsigned int* distance, int* reachable, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<SSSP_vertex_type, int> G;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  CountingSSSP b;
+  auto tmp = GraphMat::graph_program_init(b, G);
+  SSSP_vertex_type init;
+  init.distance = 0;
+  SSSP_vertex_type inf;
+  G.setAllVertexproperty(inf);
+  G.setAllInactive();
+  G.setVertexproperty(source, init);
+  G.setActive(source);
+  double t0 = now_ms();
+  GraphMat::run_graph_program(&b, G, GraphMat::UNTIL_CONVERGENCE, &tmp);
+  if (ms) *ms = now_ms() - t0;
+  int r = 0;
+  G.applyReduceAllVertices(&r, reachable_or_not);
+  if (reachable) *reachable = r;
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) distance[i - 1] = G.getVertexproperty(i).distance;
+  GraphMat::graph_program_clear(tmp);
+  return b.iters;
+}
+#endif
+
+#if defined(GM_REF_APP_DELTASTEPPING)
+// run_deltastepping, /root/reference/src/DeltaStepping.cpp:124-198 (load_edgelist
+// there does not square the matrix; neither do we).  Returns buckets processed.
+int gm_ref_deltastepping(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val,
+                         int delta, int source, unsigned int* distance, int* bucket, int* reachable, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::edgelist_t<int> E(m, n, nnz);
+  for (int i = 0; i < nnz; i++) {
+    E.edges[i].src = src[i];
+    E.edges[i].dst = dst[i];
+    E.edges[i].val = val[i];
+  }
+  auto light_edges = GraphMat::filter_edges(&E, less_than_delta, &delta);
+  auto heavy_edges = GraphMat::filter_edges(&E, greater_than_delta, &delta);
+  E.clear();
+  GraphMat::Graph<DeltaSteppingDS> G;
+  G.ReadEdgelist(light_edges);
+  GraphMat::Graph<DeltaSteppingDS> G2;
+  G2.ReadEdgelist(heavy_edges);
+  light_edges.clear();
+  heavy_edges.clear();
+  G2.shareVertexProperty(G);
+  DeltaStepping deltastep(delta);
+  auto ds_ts = GraphMat::graph_program_init(deltastep, G);
+  G.setAllInactive();
+  DeltaSteppingDS v;
+  v.distance = 0;
+  v.bucket = 0;
+  G.setVertexproperty(source, v);
+  G.setActive(source);
+  int bucket_not_empty = 1;
+  double t0 = now_ms();
+  do {
+    G.setAllActive();
+    GraphMat::run_graph_program(&deltastep, G, GraphMat::UNTIL_CONVERGENCE, &ds_ts);
+    G2.setAllActive();
+    GraphMat::run_graph_program(&deltastep, G2, 1, &ds_ts);
+    deltastep.bid++;
+    bucket_not_empty = 0;
+    G.applyReduceAllVertices(&bucket_not_empty, CheckBucketNotEmpty, Add<int>, (void*)&deltastep.bid);
+  } while (bucket_not_empty != 0);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(ds_ts);
+  int r = 0;
+  G.applyReduceAllVertices(&r, reachable_or_not);
+  if (reachable) *reachable = r;
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    DeltaSteppingDS p = G.getVertexproperty(i);
+    distance[i - 1] = p.distance;
+    if (bucket) bucket[i - 1] = p.bucket;
+  }
+  return deltastep.bid;
+}
+#endif
+
+#if defined(GM_REF_APP_SGD)
+// run_sgd, /root/reference/src/SGD.cpp:163-224, with K a template argument (the app
+// hard-codes 20 at :164; BASELINE's SGD config asks for 32).  lv is n*K doubles,
+// row-major by public vertex id; rmse[0] / rmse[1] = before / after.
+}  // extern "C" (templates need C++ linkage)
+template <int K>
+int sgd_impl(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val, int iterations,
+             double lambda, double step, double* lv, double* rmse, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<LatentVector<K> > G;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  SGDProgram<K> sgdp(lambda, step);
+  RMSEProgram<K> rmsep;
+  auto sgdp_tmp = GraphMat::graph_program_init(sgdp, G);
+  auto rmsep_tmp = GraphMat::graph_program_init(rmsep, G);
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    LatentVector<K> v;
+    v.sqerr = 0.0;
+    unsigned int r = i;
+    for (int j = 0; j < K; j++) v.lv[j] = ((double)rand_r(&r) / (double)RAND_MAX);
+    G.setVertexproperty(i, v);
+  }
+  G.setAllActive();
+  GraphMat::run_graph_program(&rmsep, G, 1, &rmsep_tmp);
+  double err = 0.0;
+  G.applyReduceAllVertices(&err, return_sqerr, GraphMat::AddFn);
+  rmse[0] = sqrt(err / (G.nnz));
+  double t0 = now_ms();
+  G.setAllActive();
+  GraphMat::run_graph_program(&sgdp, G, iterations, &sgdp_tmp);
+  if (ms) *ms = now_ms() - t0;
+  G.setAllActive();
+  GraphMat::run_graph_program(&rmsep, G, 1, &rmsep_tmp);
+  GraphMat::graph_program_clear(rmsep_tmp);
+  GraphMat::graph_program_clear(sgdp_tmp);
+  err = 0.0;
+  G.applyReduceAllVertices(&err, return_sqerr, GraphMat::AddFn);
+  rmse[1] = sqrt(err / (G.nnz));
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    LatentVector<K> p = G.getVertexproperty(i);
+    for (int j = 0; j < K; j++) lv[(size_t)(i - 1) * K + j] = p.lv[j];
+  }
+  return iterations;
+}
+extern "C" {
+int gm_ref_sgd(int threads, int K, int m, int n, int nnz, const int* src, const int* dst, const int* val,
+               int iterations, double lambda, double step, double* lv, double* rmse, double* ms) {
+  if (K == 20) return sgd_impl<20>(threads, m, n, nnz, src, dst, val, iterations, lambda, step, lv, rmse, ms);
+  if (K == 32) return sgd_impl<32>(threads, m, n, nnz, src, dst, val, iterations, lambda, step, lv, rmse, ms);
+  if (K == 4) return sgd_impl<4>(threads, m, n, nnz, src, dst, val, iterations, lambda, step, lv, rmse, ms);
+  return -1;
+}
+#endif
+
+}  // extern "C"
