@@ -1,0 +1,153 @@
+// gm_builtin.cu -- the five vertex programs BASELINE.json names, instantiated over the
+// device engine and exported through the C ABI (gm_run_program / gm_step_*).
+// The programs themselves are in graphmat_b200/include/GraphMat/programs/ and cite the
+// reference app lines they restate (narayanan2004/GraphMat src/{PageRank,BFS,SSSP,
+// DeltaStepping,SGD}.cpp).
+#include <cstring>
+
+#include "GraphMat/gm_engine.cuh"
+#include "GraphMat/programs/BFS.h"
+#include "GraphMat/programs/PageRank.h"
+#include "GraphMat/programs/SGD.h"
+#include "GraphMat/programs/SSSP.h"
+#include "gm_internal.h"
+
+namespace {
+
+// state block <-> program object
+template <class P> struct binder;
+template <> struct binder<Degree<PR, int> > {
+  static int bytes() { return 0; }
+  static void in(Degree<PR, int>&, const void*) {}
+  static void out(const Degree<PR, int>&, void*) {}
+};
+template <> struct binder<PageRank<int> > {
+  static int bytes() { return sizeof(gm_pagerank_state); }
+  static void in(PageRank<int>& p, const void* s) { if (s) p.alpha = ((const gm_pagerank_state*)s)->alpha; }
+  static void out(const PageRank<int>&, void*) {}
+};
+template <> struct binder<BFS2> {
+  static int bytes() { return sizeof(gm_bfs_state); }
+  static void in(BFS2& p, const void* s) { if (s) p.current_depth = ((const gm_bfs_state*)s)->current_depth; }
+  static void out(const BFS2& p, void* s) { if (s) ((gm_bfs_state*)s)->current_depth = p.current_depth; }
+};
+template <> struct binder<SSSP<int> > {
+  static int bytes() { return 0; }
+  static void in(SSSP<int>&, const void*) {}
+  static void out(const SSSP<int>&, void*) {}
+};
+template <> struct binder<DeltaStepping> {
+  static int bytes() { return sizeof(gm_deltastepping_state); }
+  static void in(DeltaStepping& p, const void* s) {
+    if (s) { p.delta = ((const gm_deltastepping_state*)s)->delta; p.bid = ((const gm_deltastepping_state*)s)->bid; }
+  }
+  static void out(const DeltaStepping& p, void* s) {
+    if (s) { ((gm_deltastepping_state*)s)->delta = p.delta; ((gm_deltastepping_state*)s)->bid = p.bid; }
+  }
+};
+template <unsigned K> struct binder<SGDProgram<K> > {
+  static int bytes() { return sizeof(gm_sgd_state); }
+  static void in(SGDProgram<K>& p, const void* s) {
+    if (s) { p.lambda = ((const gm_sgd_state*)s)->lambda; p.step = ((const gm_sgd_state*)s)->step; }
+  }
+  static void out(const SGDProgram<K>&, void*) {}
+};
+template <unsigned K> struct binder<RMSEProgram<K> > {
+  static int bytes() { return 0; }
+  static void in(RMSEProgram<K>&, const void*) {}
+  static void out(const RMSEProgram<K>&, void*) {}
+};
+
+enum { OP_RUN, OP_SEND, OP_SPMSPV, OP_APPLY, OP_SIZES };
+struct call {
+  int op;
+  gm_graph* g;
+  void* state;
+  int iterations;
+  gm_vectors* tmp;
+  gm_run_stats* stats;
+  int* changed;
+  int *sT, *sU, *sV, *sS;
+};
+
+template <class P>
+int dispatch(const call& c) {
+  typedef gm::engine<P> EN;
+  if (c.op == OP_SIZES) {
+    *c.sT = (int)sizeof(typename EN::T);
+    *c.sU = (int)sizeof(typename EN::U);
+    *c.sV = (int)sizeof(typename EN::V);
+    *c.sS = binder<P>::bytes();
+    return 0;
+  }
+  P prog;
+  binder<P>::in(prog, c.state);
+  if (c.op == OP_RUN) {
+    int rc = EN::run(prog, c.g, c.iterations, c.tmp, c.stats);
+    binder<P>::out(prog, c.state);
+    return rc;
+  }
+  gm_graph_view gv;
+  gm_vectors_view vv;
+  if (gm_graph_view_get(c.g, &gv) || gm_vectors_view_get(c.tmp, &vv) || EN::check(gv, vv)) return 1;
+  cudaStream_t st = (cudaStream_t)gv.stream;
+  if (c.op == OP_SEND) {
+    if (EN::send(prog, gv, vv, nullptr)) return 1;
+    if (gv.world > 1 && gm_graph_exchange_x(c.g, c.tmp)) return 1;
+  } else if (c.op == OP_SPMSPV) {
+    if (EN::spmspv(prog, gv, vv, false, nullptr)) return 1;
+  } else {
+    if (cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st) != cudaSuccess) return 1;
+    if (EN::apply(prog, gv, vv, nullptr)) return 1;
+    if (cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) {
+    gm_set_error("kernel failed");
+    return 1;
+  }
+  if (c.op == OP_APPLY && c.changed) *c.changed = gv.h_flags[0];
+  return 0;
+}
+
+int route(int program, const call& c) {
+  switch (program) {
+    case GM_PROG_DEGREE: return dispatch<Degree<PR, int> >(c);
+    case GM_PROG_PAGERANK: return dispatch<PageRank<int> >(c);
+    case GM_PROG_BFS: return dispatch<BFS2>(c);
+    case GM_PROG_SSSP: return dispatch<SSSP<int> >(c);
+    case GM_PROG_DELTASTEPPING: return dispatch<DeltaStepping>(c);
+    case GM_PROG_SGD20: return dispatch<SGDProgram<20> >(c);
+    case GM_PROG_RMSE20: return dispatch<RMSEProgram<20> >(c);
+    case GM_PROG_SGD32: return dispatch<SGDProgram<32> >(c);
+    case GM_PROG_RMSE32: return dispatch<RMSEProgram<32> >(c);
+    case GM_PROG_SGD4: return dispatch<SGDProgram<4> >(c);
+    case GM_PROG_RMSE4: return dispatch<RMSEProgram<4> >(c);
+  }
+  gm_set_error("unknown program id");
+  return 1;
+}
+
+}  // namespace
+
+extern "C" int gm_program_sizes(int program, int* sizeof_T, int* sizeof_U, int* sizeof_V, int* sizeof_state) {
+  int a, b, c2, d;
+  call c = {OP_SIZES, nullptr, nullptr, 0, nullptr, nullptr, nullptr, sizeof_T ? sizeof_T : &a, sizeof_U ? sizeof_U : &b,
+            sizeof_V ? sizeof_V : &c2, sizeof_state ? sizeof_state : &d};
+  return route(program, c);
+}
+extern "C" int gm_run_program(gm_graph* g, int program, void* state, int iterations, gm_vectors* tmp, gm_run_stats* stats) {
+  call c = {OP_RUN, g, state, iterations, tmp, stats, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return route(program, c);
+}
+extern "C" int gm_step_send(gm_graph* g, int program, const void* state, gm_vectors* tmp) {
+  call c = {OP_SEND, g, const_cast<void*>(state), 0, tmp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return route(program, c);
+}
+extern "C" int gm_step_spmspv(gm_graph* g, int program, const void* state, gm_vectors* tmp) {
+  call c = {OP_SPMSPV, g, const_cast<void*>(state), 0, tmp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return route(program, c);
+}
+extern "C" int gm_step_apply(gm_graph* g, int program, void* state, gm_vectors* tmp, int* changed) {
+  call c = {OP_APPLY, g, state, 0, tmp, nullptr, changed, nullptr, nullptr, nullptr, nullptr};
+  return route(program, c);
+}

@@ -1,0 +1,871 @@
+// gm_core.cu -- graph container + device-side matrix construction behind the C ABI
+// (include/graphmat_b200.h).
+//
+// Replaces the reference's Graph::ReadEdgelist (include/Graph.h:210-246),
+// SpMat::ingestEdgelist + DCSCTile ctor + Transpose (include/GMDP/matrices/SpMat.h:97-278,
+// 422-443, DCSCTile.h:241-381) and the Graph accessors (include/Graph.h:263-364) of
+// narayanan2004/GraphMat -- NOT by translating them: everything is built on the device
+// with radix sorts, into the row-sorted CSR + sliced-ELL layout the kernels in
+// gm_engine.cuh stream ("Data layout in HBM").
+//
+// What is kept from the reference is the LOGICAL layout that fixes results:
+//   * public id -> native id permutation (Graph.h:111-130) with ref_threads
+//   * per row, entries in ascending native column id (the fold order of
+//     GMDP/singlenode/spmspv.h:55-77)
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gm_internal.h"
+
+static thread_local std::string g_err;
+void gm_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* gm_last_error(void) { return g_err.c_str(); }
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char b_[512];                                                                          \
+      snprintf(b_, sizeof b_, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      gm_set_error(b_);                                                                      \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+template <class T>
+static int dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return 0;
+}
+
+// --------------------------------------------------------------- id mapping --
+// include/Graph.h:111-130 with nsegments = 1 (parity target is the 1-rank reference)
+__host__ __device__ static inline int to_native0(int pub1, int n, int npart) {
+  int v = pub1 - 1;
+  int height = n / npart;
+  int vmax = height * npart;
+  if (v >= vmax) return v;
+  int col = v % npart;
+  int row = v / npart;
+  return row + col * height;
+}
+
+__global__ void k_to_native(int* ids, long long nnz, int n, int npart) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < nnz) ids[e] = to_native0(ids[e], n, npart);
+}
+
+__global__ void k_hist(const int* ids, long long nnz, int* cnt) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(cnt + ids[e], 1);
+}
+
+__global__ void k_vertex_keys(const int* deg, int n, unsigned long long* keys) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) keys[v] = ((unsigned long long)(0xffffffffu - (unsigned)deg[v]) << 32) | (unsigned)v;
+}
+
+// placement p (hot first) -> owner p % world, local p / world, x index owner * n_pad + local
+__global__ void k_place(const unsigned long long* keys, int n, int world, int n_pad, int* xidx_of_native) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) xidx_of_native[(unsigned)(keys[p] & 0xffffffffu)] = (p % world) * n_pad + p / world;
+}
+
+__global__ void k_count_owned(const int* rows, long long nnz, const int* xidx, int n_pad, int rank, int* len_local) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int xr = xidx[rows[e]];
+  if (xr / n_pad == rank) atomicAdd(len_local + (xr % n_pad), 1);
+}
+
+__global__ void k_slot_from_keys(const unsigned long long* keys, int n_pad, const int* len_local, int* slot_vertex,
+                                 int* slot_of_local, int* row_len) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_pad) return;
+  int local = (int)(keys[s] & 0xffffffffu);
+  slot_vertex[s] = local;
+  slot_of_local[local] = s;
+  row_len[s] = len_local[local];
+}
+
+__global__ void k_edge_keys(const int* rows, const int* cols, long long nnz, const int* xidx, int n_pad, int rank,
+                            const int* slot_of_local, unsigned long long* keys, unsigned* payload) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int xr = xidx[rows[e]];
+  unsigned long long k = ~0ull;
+  if (xr / n_pad == rank) {
+    int local = xr % n_pad;
+    int slot = slot_of_local ? slot_of_local[local] : local;
+    k = ((unsigned long long)(unsigned)slot << 32) | (unsigned)cols[e];
+  }
+  keys[e] = k;
+  payload[e] = (unsigned)e;
+}
+
+__global__ void k_len_to_ll(const int* len, int n, long long* out, int mul) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (long long)len[i] * mul;
+}
+
+__global__ void k_count_heavy(const int* row_len, int n, int thr, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool h = i < n && row_len[i] > thr;
+  unsigned m = __ballot_sync(0xffffffffu, h);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
+__global__ void k_count_nonzero(const int* row_len, int n, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool h = i < n && row_len[i] > 0;
+  unsigned m = __ballot_sync(0xffffffffu, h);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
+__global__ void k_slice_width(const int* row_len, int n_heavy, int n_slices, long long* out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_slices) out[s] = 32ll * row_len[n_heavy + s * 32];
+}
+
+template <class E>
+__global__ void k_fill_heavy(const unsigned long long* keys, const unsigned* payload, long long cnt, const int* xidx,
+                             const E* val, int* h_col, E* h_val) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  h_col[i] = xidx[(unsigned)(keys[i] & 0xffffffffu)];
+  h_val[i] = val ? val[payload[i]] : E(1);
+}
+
+template <class E>
+__global__ void k_fill_sell(const unsigned long long* keys, const unsigned* payload, long long first, long long cnt,
+                            const int* xidx, const E* val, const long long* row_ptr, const long long* slice_ptr,
+                            int n_heavy, int* s_col, E* s_val) {
+  long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  unsigned long long k = keys[i];
+  int slot = (int)(k >> 32);
+  long long j = i - row_ptr[slot];
+  int rel = slot - n_heavy;
+  long long pos = slice_ptr[rel >> 5] + j * 32 + (rel & 31);
+  s_col[pos] = xidx[(unsigned)(k & 0xffffffffu)];
+  s_val[pos] = val ? val[payload[i]] : E(1);
+}
+
+// ------------------------------------------------------------ RMAT generator --
+__host__ __device__ static inline unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// Graph500 quadrant probabilities a,b,c,d = .57,.19,.19,.05 as 32-bit thresholds
+#define GM_RMAT_TA 2448131358u  /* floor(0.57 * 2^32) */
+#define GM_RMAT_TAB 3264175145u /* floor(0.76 * 2^32) */
+#define GM_RMAT_TABC 4080218931u /* floor(0.95 * 2^32) */
+__host__ __device__ static inline void rmat_edge(int scale, unsigned long long seed, unsigned long long e, int* s,
+                                                 int* d) {
+  unsigned si = 0, di = 0;
+  unsigned long long h = 0;
+  for (int l = 0; l < scale; l++) {
+    if ((l & 1) == 0) h = splitmix64(seed * 0x100000001B3ull + e * 32ull + (unsigned long long)(l >> 1));
+    unsigned r = (l & 1) ? (unsigned)(h >> 32) : (unsigned)h;
+    unsigned sb = r >= GM_RMAT_TAB;                                  // quadrants c, d
+    unsigned db = (r >= GM_RMAT_TA && r < GM_RMAT_TAB) || r >= GM_RMAT_TABC;  // quadrants b, d
+    si = (si << 1) | sb;
+    di = (di << 1) | db;
+  }
+  *s = (int)si + 1;
+  *d = (int)di + 1;
+}
+__host__ __device__ static inline int rmat_weight(unsigned long long wseed, unsigned long long e, int weight_max) {
+  if (weight_max <= 0) return 1;
+  return 1 + (int)(splitmix64(wseed * 0x9E3779B1ull + e + 0x5555555555ull) % (unsigned long long)weight_max);
+}
+__global__ void k_rmat(int scale, unsigned long long seed, int weight_max, unsigned long long wseed, long long nnz,
+                       int* src, int* dst, int* val) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int s, d;
+  rmat_edge(scale, seed, (unsigned long long)e, &s, &d);
+  src[e] = s;
+  dst[e] = d;
+  if (val) val[e] = rmat_weight(wseed, (unsigned long long)e, weight_max);
+}
+
+extern "C" int gm_rmat_edges_host(int scale, int edge_factor, unsigned long long seed, int weight_max,
+                                  unsigned long long weight_seed, int* src, int* dst, int* val) {
+  long long nnz = (long long)edge_factor << scale;
+#pragma omp parallel for
+  for (long long e = 0; e < nnz; e++) {
+    rmat_edge(scale, seed, (unsigned long long)e, &src[e], &dst[e]);
+    if (val) val[e] = rmat_weight(weight_seed, (unsigned long long)e, weight_max);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------- device utils --
+extern "C" int gm_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return 0;
+}
+extern "C" int gm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static inline unsigned nblk(long long n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+static int ceil_log2(long long v) {
+  int b = 0;
+  while ((1ll << b) < v) b++;
+  return b;
+}
+
+template <class K, class V>
+static int sort_pairs(K* k0, K* k1, V* v0, V* v1, long long n, int end_bit, cudaStream_t st, K** kout, V** vout) {
+  cub::DoubleBuffer<K> kb(k0, k1);
+  cub::DoubleBuffer<V> vb(v0, v1);
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, n, 0, end_bit, st));
+  void* tmp = nullptr;
+  CK(cudaMalloc(&tmp, tb ? tb : 1));
+  CK(cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, n, 0, end_bit, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(tmp));
+  *kout = kb.Current();
+  *vout = vb.Current();
+  return 0;
+}
+
+template <class K>
+static int sort_keys(K* k0, K* k1, long long n, int end_bit, cudaStream_t st, K** kout) {
+  cub::DoubleBuffer<K> kb(k0, k1);
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, kb, n, 0, end_bit, st));
+  void* tmp = nullptr;
+  CK(cudaMalloc(&tmp, tb ? tb : 1));
+  CK(cub::DeviceRadixSort::SortKeys(tmp, tb, kb, n, 0, end_bit, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(tmp));
+  *kout = kb.Current();
+  return 0;
+}
+
+static int exclusive_scan_ll(const long long* in, long long* out, int n, cudaStream_t st) {
+  // out has n + 1 entries; out[n] = total
+  size_t tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n + 1, st));
+  void* tmp = nullptr;
+  CK(cudaMalloc(&tmp, tb ? tb : 1));
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n + 1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(tmp));
+  return 0;
+}
+
+// ------------------------------------------------------------- matrix build --
+static void matrix_free(gm_matrix& M) {
+  cudaFree(M.slot_vertex);
+  cudaFree(M.row_len);
+  cudaFree(M.h_ptr);
+  cudaFree(M.h_col);
+  cudaFree(M.h_val);
+  cudaFree(M.slice_ptr);
+  cudaFree(M.s_col);
+  cudaFree(M.s_val);
+  M = gm_matrix();
+}
+
+// rows/cols: native 0-based ids per edge (device); val: edge values or NULL (all ones)
+template <class E>
+static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* cols, const E* val, long long nnz,
+                        bool identity) {
+  cudaStream_t st = g->stream;
+  const int n_pad = g->n_pad;
+  int* len_local = nullptr;
+  if (dalloc(&len_local, n_pad)) return 1;
+  CK(cudaMemsetAsync(len_local, 0, (size_t)n_pad * 4, st));
+  if (nnz) k_count_owned<<<nblk(nnz), 256, 0, st>>>(rows, nnz, g->d_xidx, n_pad, g->rank, len_local);
+
+  int* slot_of_local = nullptr;
+  if (dalloc(&M.row_len, n_pad)) return 1;
+  if (identity) {
+    CK(cudaMemcpyAsync(M.row_len, len_local, (size_t)n_pad * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    unsigned long long *k0, *k1, *ks;
+    if (dalloc(&k0, n_pad) || dalloc(&k1, n_pad)) return 1;
+    k_vertex_keys<<<nblk(n_pad), 256, 0, st>>>(len_local, n_pad, k0);
+    if (sort_keys(k0, k1, n_pad, 64, st, &ks)) return 1;
+    if (dalloc(&M.slot_vertex, n_pad) || dalloc(&slot_of_local, n_pad)) return 1;
+    k_slot_from_keys<<<nblk(n_pad), 256, 0, st>>>(ks, n_pad, len_local, M.slot_vertex, slot_of_local, M.row_len);
+    CK(cudaStreamSynchronize(st));
+    cudaFree(k0);
+    cudaFree(k1);
+  }
+
+  // row_ptr by slot
+  long long *len_ll = nullptr, *row_ptr = nullptr;
+  if (dalloc(&len_ll, (size_t)n_pad + 1) || dalloc(&row_ptr, (size_t)n_pad + 1)) return 1;
+  CK(cudaMemsetAsync(len_ll, 0, ((size_t)n_pad + 1) * 8, st));
+  k_len_to_ll<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, len_ll, 1);
+  if (exclusive_scan_ll(len_ll, row_ptr, n_pad, st)) return 1;
+  long long owned = 0;
+  CK(cudaMemcpy(&owned, row_ptr + n_pad, 8, cudaMemcpyDeviceToHost));
+  M.nnz = owned;
+
+  // heavy prefix / non-empty prefix
+  int* cnt = nullptr;
+  if (dalloc(&cnt, 2)) return 1;
+  CK(cudaMemsetAsync(cnt, 0, 8, st));
+  k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, g->heavy_threshold, cnt);
+  k_count_nonzero<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, cnt + 1);
+  int hc[2];
+  CK(cudaMemcpy(hc, cnt, 8, cudaMemcpyDeviceToHost));
+  cudaFree(cnt);
+  int n_heavy = std::min(n_pad, (hc[0] + 31) / 32 * 32);
+  int n_nonzero = hc[1];
+  int n_slices = n_nonzero > n_heavy ? (n_nonzero - n_heavy + 31) / 32 : 0;
+  M.n_slots = n_pad;
+  M.n_heavy = n_heavy;
+  M.n_slices = n_slices;
+  M.identity = identity ? 1 : 0;
+
+  // sort owned edges by (slot, native column)
+  unsigned long long *k0 = nullptr, *k1 = nullptr, *ks = nullptr;
+  unsigned *p0 = nullptr, *p1 = nullptr, *ps = nullptr;
+  if (dalloc(&k0, nnz) || dalloc(&k1, nnz) || dalloc(&p0, nnz) || dalloc(&p1, nnz)) return 1;
+  if (nnz) {
+    k_edge_keys<<<nblk(nnz), 256, 0, st>>>(rows, cols, nnz, g->d_xidx, n_pad, g->rank, slot_of_local, k0, p0);
+    // the unowned sentinel ~0 needs all 64 bits only when some edge is unowned
+    int end_bit = (g->world > 1) ? 64 : 32 + std::max(1, ceil_log2(n_pad));
+    if (sort_pairs(k0, k1, p0, p1, nnz, end_bit, st, &ks, &ps)) return 1;
+  }
+
+  // heavy rows: the sorted prefix is already row-contiguous
+  long long nh = 0;
+  if (dalloc(&M.h_ptr, (size_t)n_heavy + 1)) return 1;
+  CK(cudaMemcpyAsync(M.h_ptr, row_ptr, ((size_t)n_heavy + 1) * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpy(&nh, row_ptr + n_heavy, 8, cudaMemcpyDeviceToHost));
+  E* hv = nullptr;
+  if (dalloc(&M.h_col, nh) || dalloc(&hv, nh)) return 1;
+  M.h_val = hv;
+  if (nh) k_fill_heavy<E><<<nblk(nh), 256, 0, st>>>(ks, ps, nh, g->d_xidx, val, M.h_col, hv);
+
+  // sliced ELL for the rest
+  long long* widths = nullptr;
+  if (dalloc(&widths, (size_t)n_slices + 1) || dalloc(&M.slice_ptr, (size_t)n_slices + 1)) return 1;
+  CK(cudaMemsetAsync(widths, 0, ((size_t)n_slices + 1) * 8, st));
+  if (n_slices) k_slice_width<<<nblk(n_slices), 256, 0, st>>>(M.row_len, n_heavy, n_slices, widths);
+  if (exclusive_scan_ll(widths, M.slice_ptr, n_slices, st)) return 1;
+  long long total = 0;
+  CK(cudaMemcpy(&total, M.slice_ptr + n_slices, 8, cudaMemcpyDeviceToHost));
+  E* sv = nullptr;
+  if (dalloc(&M.s_col, total) || dalloc(&sv, total)) return 1;
+  M.s_val = sv;
+  M.s_entries = total;
+  CK(cudaMemsetAsync(M.s_col, 0, (size_t)total * 4, st));
+  CK(cudaMemsetAsync(sv, 0, (size_t)total * sizeof(E), st));
+  if (owned > nh)
+    k_fill_sell<E><<<nblk(owned - nh), 256, 0, st>>>(ks, ps, nh, owned, g->d_xidx, val, row_ptr, M.slice_ptr, n_heavy,
+                                                    M.s_col, sv);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaFree(widths);
+  cudaFree(k0);
+  cudaFree(k1);
+  cudaFree(p0);
+  cudaFree(p1);
+  cudaFree(len_ll);
+  cudaFree(row_ptr);
+  cudaFree(len_local);
+  cudaFree(slot_of_local);
+  return 0;
+}
+
+static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
+  v->n_slots = M.n_slots;
+  v->n_heavy = M.n_heavy;
+  v->n_slices = M.n_slices;
+  v->identity = M.identity;
+  v->slot_vertex = M.slot_vertex;
+  v->row_len = M.row_len;
+  v->h_ptr = M.h_ptr;
+  v->h_col = M.h_col;
+  v->h_val = M.h_val;
+  v->slice_ptr = M.slice_ptr;
+  v->s_col = M.s_col;
+  v->s_val = M.s_val;
+  v->nnz = M.nnz;
+}
+
+// d_src/d_dst: device copies owned by this call (public ids, overwritten with native ids)
+template <class E>
+static int build_graph(gm_graph* g, int* d_src, int* d_dst, const E* d_val, long long nnz, const gm_graph* like,
+                       int build_mask) {
+  cudaStream_t st = g->stream;
+  const int n = g->n;
+  const int npart = g->ref_threads * 16;
+  // first public vertex with an out-edge (the benchmark's BFS/SSSP source)
+  g->first_source = 0;
+  if (nnz) {
+    int* dmin;
+    if (dalloc(&dmin, 1)) return 1;
+    size_t tb = 0;
+    CK(cub::DeviceReduce::Min(nullptr, tb, d_src, dmin, nnz, st));
+    void* tmp;
+    CK(cudaMalloc(&tmp, tb ? tb : 1));
+    CK(cub::DeviceReduce::Min(tmp, tb, d_src, dmin, nnz, st));
+    CK(cudaMemcpy(&g->first_source, dmin, 4, cudaMemcpyDeviceToHost));
+    cudaFree(tmp);
+    cudaFree(dmin);
+    k_to_native<<<nblk(nnz), 256, 0, st>>>(d_src, nnz, n, npart);
+    k_to_native<<<nblk(nnz), 256, 0, st>>>(d_dst, nnz, n, npart);
+  }
+  if (dalloc(&g->d_xidx, n)) return 1;
+  if (like) {
+    if (like->n != n || like->world != g->world || like->ref_threads != g->ref_threads) {
+      gm_set_error("order_like graph has a different shape");
+      return 1;
+    }
+    CK(cudaMemcpyAsync(g->d_xidx, like->d_xidx, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    // placement: vertices by decreasing in-degree (= AT row length), ties by native id
+    int* indeg;
+    unsigned long long *k0, *k1, *ks;
+    if (dalloc(&indeg, n) || dalloc(&k0, n) || dalloc(&k1, n)) return 1;
+    CK(cudaMemsetAsync(indeg, 0, (size_t)n * 4, st));
+    if (nnz) k_hist<<<nblk(nnz), 256, 0, st>>>(d_dst, nnz, indeg);
+    k_vertex_keys<<<nblk(n), 256, 0, st>>>(indeg, n, k0);
+    if (sort_keys(k0, k1, n, 64, st, &ks)) return 1;
+    k_place<<<nblk(n), 256, 0, st>>>(ks, n, g->world, g->n_pad, g->d_xidx);
+    CK(cudaStreamSynchronize(st));
+    cudaFree(indeg);
+    cudaFree(k0);
+    cudaFree(k1);
+  }
+  if (build_mask & 2)
+    if (build_matrix<E>(g, g->AT, d_dst, d_src, d_val, nnz, like == nullptr)) return 1;
+  if (build_mask & 1)
+    if (build_matrix<E>(g, g->A, d_src, d_dst, d_val, nnz, false)) return 1;
+  return 0;
+}
+
+static int graph_common_alloc(gm_graph* g) {
+  cudaStream_t st = g->stream;
+  CK(cudaMalloc(&g->vp, (size_t)g->n_pad * g->sizeof_V));
+  CK(cudaMemsetAsync(g->vp, 0, (size_t)g->n_pad * g->sizeof_V, st));
+  g->vp_owner = true;
+  if (dalloc(&g->active, (size_t)(g->n_pad >> 5))) return 1;
+  CK(cudaMemsetAsync(g->active, 0, (size_t)(g->n_pad >> 5) * 4, st));  // active->setAll(false), Graph.h:236-237
+  if (dalloc(&g->d_flags, 16)) return 1;
+  CK(cudaMemsetAsync(g->d_flags, 0, 64, st));
+  CK(cudaMallocHost((void**)&g->h_flags, 64));
+  memset(g->h_flags, 0, 64);
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static gm_graph* graph_new(int nvertices, int sizeof_E, int sizeof_V, const gm_graph_opts* opts) {
+  gm_graph* g = new gm_graph();
+  g->n = nvertices;
+  g->sizeof_E = sizeof_E;
+  g->sizeof_V = sizeof_V;
+  g->ref_threads = (opts && opts->ref_threads > 0) ? opts->ref_threads : 4;
+  g->rank = opts ? opts->rank : 0;
+  g->world = (opts && opts->world > 0) ? opts->world : 1;
+  g->heavy_threshold = (opts && opts->heavy_threshold > 0) ? opts->heavy_threshold : GM_DEFAULT_HEAVY_THRESHOLD;
+  int per = (nvertices + g->world - 1) / g->world;
+  g->n_pad = std::max(32, (per + 31) / 32 * 32);
+  g->n_local = nvertices > g->rank ? (nvertices - g->rank + g->world - 1) / g->world : 0;
+  g->n_full = g->n_pad * g->world;
+  return g;
+}
+
+extern "C" int gm_graph_create(gm_graph** out, int nvertices, long long nnz, const int* src, const int* dst,
+                               const void* val, int sizeof_E, int sizeof_V, const gm_graph_opts* opts) {
+  *out = nullptr;
+  if (nvertices <= 0 || nnz < 0 || nnz >= (1ll << 32)) {
+    gm_set_error("gm_graph_create: bad nvertices/nnz");
+    return 1;
+  }
+  if (sizeof_E != 4) {
+    gm_set_error("gm_graph_create: only 4-byte edge values are supported (the five programs use E = int)");
+    return 1;
+  }
+  if (sizeof_V <= 0 || sizeof_V % 4) {
+    gm_set_error("gm_graph_create: sizeof_V must be a positive multiple of 4");
+    return 1;
+  }
+  gm_graph* g = graph_new(nvertices, sizeof_E, sizeof_V, opts);
+  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  g->nnz = nnz;
+  int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
+  if (dalloc(&d_src, nnz) || dalloc(&d_dst, nnz)) return 1;
+  cudaMemcpyKind kind = (opts && opts->edges_on_device) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (nnz) {
+    CK(cudaMemcpyAsync(d_src, src, (size_t)nnz * 4, kind, g->stream));
+    CK(cudaMemcpyAsync(d_dst, dst, (size_t)nnz * 4, kind, g->stream));
+    if (val) {
+      if (dalloc(&d_val, nnz)) return 1;
+      CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, kind, g->stream));
+    }
+  }
+  int mask = (opts && opts->build_mask) ? opts->build_mask : 3;
+  int rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  cudaFree(d_val);
+  if (rc || graph_common_alloc(g)) {
+    gm_graph_destroy(g);
+    return 1;
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int gm_graph_create_rmat(gm_graph** out, int scale, int edge_factor, unsigned long long seed, int weight_max,
+                                    unsigned long long weight_seed, int sizeof_V, const gm_graph_opts* opts) {
+  *out = nullptr;
+  if (scale < 1 || scale > 30 || edge_factor < 1 || ((long long)edge_factor << scale) >= (1ll << 32)) {
+    gm_set_error("gm_graph_create_rmat: bad scale/edge_factor");
+    return 1;
+  }
+  long long nnz = (long long)edge_factor << scale;
+  gm_graph* g = graph_new(1 << scale, 4, sizeof_V, opts);
+  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  g->nnz = nnz;
+  int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
+  if (dalloc(&d_src, nnz) || dalloc(&d_dst, nnz)) return 1;
+  if (weight_max > 0 && dalloc(&d_val, nnz)) return 1;
+  k_rmat<<<nblk(nnz), 256, 0, g->stream>>>(scale, seed, weight_max, weight_seed, nnz, d_src, d_dst, d_val);
+  CK(cudaGetLastError());
+  int mask = (opts && opts->build_mask) ? opts->build_mask : 3;
+  int rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  cudaFree(d_val);
+  if (rc || graph_common_alloc(g)) {
+    gm_graph_destroy(g);
+    return 1;
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int gm_graph_destroy(gm_graph* g) {
+  if (!g) return 0;
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  matrix_free(g->A);
+  matrix_free(g->AT);
+  cudaFree(g->d_xidx);
+  if (g->vp_owner) cudaFree(g->vp);
+  cudaFree(g->active);
+  cudaFree(g->d_flags);
+  if (g->h_flags) cudaFreeHost(g->h_flags);
+  cudaFree(g->staging);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  return 0;
+}
+
+extern "C" int gm_graph_view_get(const gm_graph* g, gm_graph_view* v) {
+  v->nvertices = g->n;
+  v->n_local = g->n_local;
+  v->n_local_pad = g->n_pad;
+  v->n_full = g->n_full;
+  v->rank = g->rank;
+  v->world = g->world;
+  v->ref_threads = g->ref_threads;
+  v->sizeof_V = g->sizeof_V;
+  v->sizeof_E = g->sizeof_E;
+  v->nnz = g->nnz;
+  v->vertexproperty = g->vp;
+  v->active_bits = g->active;
+  fill_view(g->A, &v->A);
+  fill_view(g->AT, &v->AT);
+  v->d_flags = g->d_flags;
+  v->h_flags = g->h_flags;
+  v->stream = (void*)g->stream;
+  return 0;
+}
+
+extern "C" int gm_graph_synchronize(const gm_graph* g) {
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+// ----------------------------------------------------------------- activity --
+__global__ void k_fill_words(unsigned* bits, int n_valid, int n_pad, unsigned fill) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (n_pad >> 5)) return;
+  int lo = w << 5;
+  unsigned v = 0;
+  if (lo + 32 <= n_valid) v = 0xffffffffu;
+  else if (lo < n_valid) v = (1u << (n_valid - lo)) - 1u;
+  bits[w] = v & fill;
+}
+__global__ void k_set_bit(unsigned* bits, int i, int on) {
+  if (on) atomicOr(bits + (i >> 5), 1u << (i & 31));
+  else atomicAnd(bits + (i >> 5), ~(1u << (i & 31)));
+}
+
+static int host_xidx(const gm_graph* g) {
+  gm_graph* m = const_cast<gm_graph*>(g);
+  if (m->h_xidx.empty()) {
+    m->h_xidx.resize(g->n);
+    CK(cudaMemcpy(m->h_xidx.data(), g->d_xidx, (size_t)g->n * 4, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+// public 1-based id -> (owner, local); returns 1 on a bad id
+static int locate(const gm_graph* g, int v, int* owner, int* local) {
+  if (v < 1 || v > g->n) {
+    gm_set_error("vertex id out of range (ids are 1-based)");
+    return 1;
+  }
+  if (host_xidx(g)) return 1;
+  int xi = g->h_xidx[to_native0(v, g->n, g->ref_threads * 16)];
+  *owner = xi / g->n_pad;
+  *local = xi % g->n_pad;
+  return 0;
+}
+
+extern "C" int gm_graph_set_all_active(gm_graph* g) {
+  k_fill_words<<<nblk(g->n_pad >> 5), 256, 0, g->stream>>>(g->active, g->n_local, g->n_pad, 0xffffffffu);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gm_graph_set_all_inactive(gm_graph* g) {
+  CK(cudaMemsetAsync(g->active, 0, (size_t)(g->n_pad >> 5) * 4, g->stream));
+  return 0;
+}
+static int set_active(gm_graph* g, int v, int on) {
+  int owner, local;
+  if (locate(g, v, &owner, &local)) return 1;
+  if (owner != g->rank) return 0;
+  k_set_bit<<<1, 1, 0, g->stream>>>(g->active, local, on);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gm_graph_set_active(gm_graph* g, int v) { return set_active(g, v, 1); }
+extern "C" int gm_graph_set_inactive(gm_graph* g, int v) { return set_active(g, v, 0); }
+
+extern "C" int gm_graph_vertex_owner(const gm_graph* g, int v) {
+  int owner, local;
+  if (locate(g, v, &owner, &local)) return -1;
+  return owner;
+}
+extern "C" int gm_graph_out_degree_source(const gm_graph* g, int* v) {
+  *v = g->first_source;
+  return g->first_source > 0 ? 0 : 1;
+}
+
+// ---------------------------------------------------------- vertex property --
+__global__ void k_broadcast_words(unsigned* dst, const unsigned* one, int words_per, long long total_words) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < total_words) dst[i] = one[i % words_per];
+}
+// public-order array <-> placement-order storage
+__global__ void k_permute_in(unsigned* vp, const unsigned* in, int n, int npart, const int* xidx, int n_pad, int rank,
+                             int words_per) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long pub = t / words_per;
+  int w = (int)(t % words_per);
+  if (pub >= n) return;
+  int xi = xidx[to_native0((int)pub + 1, n, npart)];
+  if (xi / n_pad != rank) return;
+  vp[(long long)(xi % n_pad) * words_per + w] = in[pub * words_per + w];
+}
+__global__ void k_permute_out(const unsigned* vp, unsigned* out, int n, int npart, const int* xidx, int n_pad, int rank,
+                              int words_per) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long pub = t / words_per;
+  int w = (int)(t % words_per);
+  if (pub >= n) return;
+  int xi = xidx[to_native0((int)pub + 1, n, npart)];
+  if (xi / n_pad != rank) return;
+  out[pub * words_per + w] = vp[(long long)(xi % n_pad) * words_per + w];
+}
+
+static int staging(gm_graph* g, size_t bytes) {
+  if (g->staging_bytes < bytes) {
+    cudaFree(g->staging);
+    g->staging = nullptr;
+    g->staging_bytes = 0;
+    CK(cudaMalloc(&g->staging, bytes));
+    g->staging_bytes = bytes;
+  }
+  return 0;
+}
+
+extern "C" int gm_graph_set_all_vertexproperty(gm_graph* g, const void* value) {
+  if (staging(g, g->sizeof_V)) return 1;
+  CK(cudaMemcpyAsync(g->staging, value, g->sizeof_V, cudaMemcpyHostToDevice, g->stream));
+  int wp = g->sizeof_V / 4;
+  long long tw = (long long)g->n_pad * wp;
+  k_broadcast_words<<<nblk(tw), 256, 0, g->stream>>>((unsigned*)g->vp, (const unsigned*)g->staging, wp, tw);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+extern "C" int gm_graph_set_vertexproperty(gm_graph* g, int v, const void* value) {
+  int owner, local;
+  if (locate(g, v, &owner, &local)) return 1;
+  if (owner != g->rank) return 0;
+  CK(cudaMemcpyAsync((char*)g->vp + (size_t)local * g->sizeof_V, value, g->sizeof_V, cudaMemcpyHostToDevice, g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+extern "C" int gm_graph_get_vertexproperty(const gm_graph* g, int v, void* value) {
+  int owner, local;
+  if (locate(g, v, &owner, &local)) return 1;
+  if (owner != g->rank) return 2;
+  CK(cudaMemcpyAsync(value, (const char*)g->vp + (size_t)local * g->sizeof_V, g->sizeof_V, cudaMemcpyDeviceToHost,
+                     g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+extern "C" int gm_graph_set_vertexproperties(gm_graph* g, const void* values) {
+  size_t bytes = (size_t)g->n * g->sizeof_V;
+  if (staging(g, bytes)) return 1;
+  CK(cudaMemcpyAsync(g->staging, values, bytes, cudaMemcpyHostToDevice, g->stream));
+  int wp = g->sizeof_V / 4;
+  long long t = (long long)g->n * wp;
+  k_permute_in<<<nblk(t), 256, 0, g->stream>>>((unsigned*)g->vp, (const unsigned*)g->staging, g->n, g->ref_threads * 16,
+                                              g->d_xidx, g->n_pad, g->rank, wp);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+extern "C" int gm_graph_get_vertexproperties(const gm_graph* g, void* values) {
+  gm_graph* m = const_cast<gm_graph*>(g);
+  size_t bytes = (size_t)g->n * g->sizeof_V;
+  if (staging(m, bytes)) return 1;
+  int wp = g->sizeof_V / 4;
+  long long t = (long long)g->n * wp;
+  if (g->world > 1) CK(cudaMemcpyAsync(m->staging, values, bytes, cudaMemcpyHostToDevice, g->stream));
+  k_permute_out<<<nblk(t), 256, 0, g->stream>>>((const unsigned*)g->vp, (unsigned*)m->staging, g->n, g->ref_threads * 16,
+                                               g->d_xidx, g->n_pad, g->rank, wp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(values, m->staging, bytes, cudaMemcpyDeviceToHost, g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+extern "C" int gm_graph_share_vertexproperty(gm_graph* g, gm_graph* owner) {
+  if (g->n != owner->n || g->n_pad != owner->n_pad || g->sizeof_V != owner->sizeof_V) {
+    gm_set_error("gm_graph_share_vertexproperty: graphs differ in shape");
+    return 1;
+  }
+  // the two graphs must agree on vertex placement: check a sample of the map
+  if (host_xidx(g) || host_xidx(owner)) return 1;
+  if (g->h_xidx != owner->h_xidx) {
+    gm_set_error("gm_graph_share_vertexproperty: create the graph with opts.order_like = owner");
+    return 1;
+  }
+  if (g->vp_owner) cudaFree(g->vp);
+  g->vp = owner->vp;
+  g->vp_owner = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------ vectors --
+extern "C" int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int sizeof_U) {
+  gm_vectors* v = new gm_vectors();
+  v->sizeof_T = sizeof_T;
+  v->sizeof_U = sizeof_U;
+  v->n_full = g->n_full;
+  v->n_pad = g->n_pad;
+  CK(cudaMalloc(&v->x_val, (size_t)g->n_full * sizeof_T));
+  CK(cudaMalloc((void**)&v->x_bits, (size_t)(g->n_full >> 5) * 4));
+  CK(cudaMalloc(&v->y_val, (size_t)g->n_pad * sizeof_U));
+  CK(cudaMalloc((void**)&v->y_bits, (size_t)(g->n_pad >> 5) * 4));
+  CK(cudaMemsetAsync(v->x_val, 0, (size_t)g->n_full * sizeof_T, g->stream));
+  CK(cudaMemsetAsync(v->x_bits, 0, (size_t)(g->n_full >> 5) * 4, g->stream));
+  CK(cudaMemsetAsync(v->y_val, 0, (size_t)g->n_pad * sizeof_U, g->stream));
+  CK(cudaMemsetAsync(v->y_bits, 0, (size_t)(g->n_pad >> 5) * 4, g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  *out = v;
+  return 0;
+}
+extern "C" int gm_vectors_destroy(gm_vectors* v) {
+  if (!v) return 0;
+  cudaFree(v->x_val);
+  cudaFree(v->x_bits);
+  cudaFree(v->y_val);
+  cudaFree(v->y_bits);
+  delete v;
+  return 0;
+}
+extern "C" int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* o) {
+  o->sizeof_T = v->sizeof_T;
+  o->sizeof_U = v->sizeof_U;
+  o->x_val = v->x_val;
+  o->x_bits = v->x_bits;
+  o->y_val = v->y_val;
+  o->y_bits = v->y_bits;
+  return 0;
+}
+
+// ----------------------------------------------------------------- exchange --
+extern "C" int gm_graph_set_exchange(gm_graph* g, gm_allgather_fn allgather, gm_allreduce_or_fn allreduce_or, void* ctx) {
+  g->allgather = allgather;
+  g->allreduce_or = allreduce_or;
+  g->xctx = ctx;
+  return 0;
+}
+extern "C" int gm_graph_exchange_x(gm_graph* g, gm_vectors* v) {
+  if (g->world == 1) return 0;
+  if (!g->allgather) {
+    gm_set_error("world > 1 but no exchange functions were registered (gm_graph_set_exchange)");
+    return 1;
+  }
+  if (g->allgather(g->xctx, v->x_val, (long long)g->n_pad * v->sizeof_T, (void*)g->stream)) return 1;
+  return g->allgather(g->xctx, v->x_bits, (long long)(g->n_pad >> 5) * 4, (void*)g->stream);
+}
+extern "C" int gm_graph_allreduce_or(gm_graph* g, int* flag) {
+  if (g->world == 1) return 0;
+  if (!g->allreduce_or) {
+    gm_set_error("world > 1 but no exchange functions were registered (gm_graph_set_exchange)");
+    return 1;
+  }
+  return g->allreduce_or(g->xctx, flag);
+}
+
+// ------------------------------------------------------------------- reduce --
+__global__ void k_reduce(const unsigned* vp, int n_local, int words_per, int what, int param, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n_local) {
+    const unsigned* p = vp + (long long)i * words_per;
+    if (what == GM_REDUCE_REACHABLE) v = p[0] < 0xffffffffu ? 1.0 : 0.0;
+    else if (what == GM_REDUCE_BUCKET_NOT_EMPTY) {
+      int b = (int)p[1];
+      v = (b >= param && b < 0x7fffffff) ? 1.0 : 0.0;
+    } else {
+      v = *reinterpret_cast<const double*>(p + words_per - 2);
+    }
+  }
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+extern "C" int gm_graph_reduce(const gm_graph* g, int what, int param, double* result) {
+  gm_graph* m = const_cast<gm_graph*>(g);
+  if (staging(m, 8)) return 1;
+  CK(cudaMemsetAsync(m->staging, 0, 8, g->stream));
+  k_reduce<<<nblk(g->n_local), 256, 0, g->stream>>>((const unsigned*)g->vp, g->n_local, g->sizeof_V / 4, what, param,
+                                                   (double*)m->staging);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(result, m->staging, 8, cudaMemcpyDeviceToHost, g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  return 0;
+}

@@ -1,0 +1,59 @@
+// gm_internal.h -- private state behind the opaque handles of include/graphmat_b200.h.
+#ifndef GM_INTERNAL_H
+#define GM_INTERNAL_H
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "graphmat_b200.h"
+
+#define GM_DEFAULT_HEAVY_THRESHOLD 4096
+
+void gm_set_error(const std::string& s);
+
+// one operand matrix (device memory owned here); see gm_matrix_view for the meaning
+struct gm_matrix {
+  int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0;
+  int* slot_vertex = nullptr;
+  int* row_len = nullptr;
+  long long* h_ptr = nullptr;
+  int* h_col = nullptr;
+  void* h_val = nullptr;
+  long long* slice_ptr = nullptr;
+  int* s_col = nullptr;
+  void* s_val = nullptr;
+  long long nnz = 0;
+  long long s_entries = 0;  // padded sliced-ELL entries
+};
+
+struct gm_graph {
+  int n = 0, n_local = 0, n_pad = 0, n_full = 0;
+  int rank = 0, world = 1, ref_threads = 4, heavy_threshold = GM_DEFAULT_HEAVY_THRESHOLD;
+  int sizeof_V = 0, sizeof_E = 4;
+  long long nnz = 0;
+  int first_source = 0;
+  int* d_xidx = nullptr;    // native id -> x index (owner * n_pad + local)
+  std::vector<int> h_xidx;  // lazily mirrored for single-vertex accessors
+  void* vp = nullptr;
+  bool vp_owner = true;
+  unsigned* active = nullptr;
+  gm_matrix A, AT;
+  int* d_flags = nullptr;
+  int* h_flags = nullptr;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+  cudaStream_t stream = nullptr;
+  gm_allgather_fn allgather = nullptr;
+  gm_allreduce_or_fn allreduce_or = nullptr;
+  void* xctx = nullptr;
+};
+
+struct gm_vectors {
+  int sizeof_T = 0, sizeof_U = 0, n_full = 0, n_pad = 0;
+  void* x_val = nullptr;
+  unsigned* x_bits = nullptr;
+  void* y_val = nullptr;
+  unsigned* y_bits = nullptr;
+};
+#endif

@@ -1,0 +1,501 @@
+// gm_engine.cuh -- the device engine behind run_graph_program: send -> generalized
+// SpMSpV -> apply, as sm_100a kernels templated on the vertex program.
+//
+// Replaces, for one rank's tile-row, the reference's
+//   IntersectReduce      include/GMDP/singlenode/intersectreduce.h:39-66   (k_send)
+//   my_spmspv / my_spmspv3  include/GMDP/singlenode/spmspv.h:39-86, spmspv3.h:38-90  (k_sell, k_heavy*)
+//   the apply loop       include/GraphMatRuntime.h:184-226                 (k_apply)
+// of narayanan2004/GraphMat.  Semantics kept bit for bit:
+//   * x bit = active bit; send_message's bool result is ignored (GraphMatRuntime.h:79-85)
+//   * per destination row the contributions are left-folded, accumulator first
+//     (SPMV.h:54-59), in ascending NATIVE column id (spmspv.h:55-77) -- the matrix
+//     build sorts every row that way, the kernels never reorder a row unless the
+//     program opts in (gm_reorderable / gm_fadd32_exact below)
+//   * apply runs only where a message arrived; "changed" is the program's operator!=
+//
+// Data layout: rows are stored by decreasing length.  The longest
+// n_heavy rows are row-contiguous and folded by one warp each (coalesced index
+// stream, gathers 32 wide); the rest are 32-row sliced-ELL, one row per lane, so a
+// lane's fold is a private sequential chain and every index load is one 128-byte
+// line per warp.  x lives in "placement" order (hot columns first) so gathers hit
+// L1/L2; none of this changes the order in which a row is folded.
+#ifndef GRAPHMAT_B200_ENGINE_CUH
+#define GRAPHMAT_B200_ENGINE_CUH
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+
+#include "GraphProgram.h"
+#include "graphmat_b200.h"
+
+namespace gm {
+
+// ------------------------------------------------------------------ traits --
+template <class T, class U, class V, class E>
+struct prog_types {
+  typedef T Tm;
+  typedef U Um;
+  typedef V Vp;
+  typedef E Ev;
+};
+template <class T, class U, class V, class E>
+prog_types<T, U, V, E> deduce_types(const GraphMat::GraphProgram<T, U, V, E>*);
+
+// A program may declare `static const bool gm_reorderable = true;` when its
+// reduce_function is associative (min, integer +, "last writer": a = b); long rows
+// are then folded as an ORDER-PRESERVING tree instead of a serial chain.
+template <class P, class = void>
+struct is_reorderable : std::false_type {};
+template <class P>
+struct is_reorderable<P, typename std::enable_if<P::gm_reorderable>::type> : std::true_type {};
+// `static const bool gm_fadd32_exact = true;`: T = U = float, process_message is
+// res = message, reduce is a += b and messages are >= 0.  Long rows then use the
+// bit-exact parallel emulation of the serial fp32 fold (k_heavy_fadd32).
+template <class P, class = void>
+struct is_fadd32 : std::false_type {};
+template <class P>
+struct is_fadd32<P, typename std::enable_if<P::gm_fadd32_exact>::type> : std::true_type {};
+
+// The program travels to the device as raw bytes: it has a vptr, and every call
+// below is qualified (P::f), so no virtual dispatch happens on the device.
+template <class P>
+struct prog_bytes {
+  alignas(16) unsigned char b[sizeof(P)];
+  __device__ __forceinline__ const P& get() const { return *reinterpret_cast<const P*>(b); }
+};
+template <class P>
+inline prog_bytes<P> pack(const P& p) {
+  prog_bytes<P> r;
+  memcpy(r.b, (const void*)&p, sizeof(P));
+  return r;
+}
+
+__device__ __forceinline__ bool test_bit(const unsigned* __restrict__ bits, int i) {
+  return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+// -------------------------------------------------------------------- send --
+// x[i] = send_message(vp[i]) where active; x bits = active bits.
+template <class P, class T, class V>
+__global__ void __launch_bounds__(256) k_send(prog_bytes<P> pb, int n_pad, const V* __restrict__ vp,
+                                              const unsigned* __restrict__ active, T* __restrict__ x,
+                                              unsigned* __restrict__ xbits) {
+  const P& prog = pb.get();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  unsigned w = active[i >> 5];
+  if ((w >> (i & 31)) & 1u) {
+    T t;
+    (void)prog.P::send_message(vp[i], t);
+    x[i] = t;
+  }
+  if ((i & 31) == 0) xbits[i >> 5] = w;
+}
+
+// ------------------------------------------------------------------- apply --
+template <class P, class U, class V>
+__global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_pad, const U* __restrict__ y,
+                                               const unsigned* __restrict__ ybits, V* __restrict__ vp,
+                                               unsigned* __restrict__ active, int* __restrict__ flags) {
+  alignas(16) unsigned char pbuf[sizeof(P)];
+  memcpy(pbuf, pb.b, sizeof(P));
+  P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  unsigned w = ybits[i >> 5];
+  bool changed = false;
+  if ((w >> (i & 31)) & 1u) {
+    V old = vp[i];
+    V cur = old;
+    prog.P::apply(y[i], cur);
+    changed = (old != cur);
+    vp[i] = cur;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, changed);
+  if ((i & 31) == 0) {
+    active[i >> 5] = m;  // setAllInactive + set where changed
+    if (m && *((volatile int*)flags) == 0) atomicExch(flags, 1);
+  }
+}
+
+__global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (n_pad >> 5)) return;
+  int lo = w << 5;
+  unsigned v = 0;
+  if (lo + 32 <= n_valid) v = 0xffffffffu;
+  else if (lo < n_valid) v = (1u << (n_valid - lo)) - 1u;
+  bits[w] = v;
+}
+
+// ------------------------------------------------------- SpMSpV: sliced ELL --
+// One row per lane.  The fold is a private left-to-right chain per lane; loads of
+// UNROLL steps are issued before they are consumed.
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+__global__ void __launch_bounds__(256)
+    k_sell(prog_bytes<P> pb, gm_matrix_view M, const T* __restrict__ x, const unsigned* __restrict__ xbits,
+           const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int* __restrict__ cols = M.s_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.s_val);
+  constexpr int UNROLL = (sizeof(T) <= 8) ? 8 : 1;
+
+  for (int s = warp; s < M.n_slices; s += nwarps) {
+    const int slot = M.n_heavy + s * 32 + lane;
+    const int len = __ldg(M.row_len + slot);
+    const long long base = __ldg(M.slice_ptr + s);
+    const int width = __shfl_sync(0xffffffffu, len, 0);  // rows are sorted: lane 0 is the longest
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    V vprop;  // V(): the dummy of SPMV.h:44 when the program does not read it
+    if (NEEDVP && len > 0) vprop = vp[vtx];
+    U acc;
+    bool have = false;
+    if (ACCUM && (IDENT || len > 0)) {  // second operand of ALL_EDGES: continue the fold held in y
+      have = test_bit(ybits, vtx);
+      if (have && len > 0) acc = y[vtx];
+    }
+    const int* cp = cols + base + lane;
+    const E* ep = vals + base + lane;
+    for (int i = 0; i < width; i += UNROLL) {
+      int c[UNROLL];
+      E ev[UNROLL];
+      bool on[UNROLL];
+      T xv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        on[u] = (i + u) < len;
+        if (on[u]) {
+          c[u] = __ldg(cp + (long long)(i + u) * 32);
+          ev[u] = ep[(long long)(i + u) * 32];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        if (on[u]) {
+          if (!ALLACT) on[u] = test_bit(xbits, c[u]);
+          if (on[u]) xv[u] = x[c[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        if (on[u]) {
+          if (have) {
+            U tmp;
+            prog.P::process_message(xv[u], ev[u], vprop, tmp);
+            prog.P::reduce_function(acc, tmp);
+          } else {
+            prog.P::process_message(xv[u], ev[u], vprop, acc);
+            have = true;
+          }
+        }
+      }
+    }
+    if (have && len > 0) y[vtx] = acc;
+    unsigned m = __ballot_sync(0xffffffffu, have);
+    if (IDENT) {
+      if (lane == 0) ybits[slot >> 5] = m;  // heavy and ELL slots never share a word
+    } else if (have && len > 0) {
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    }
+  }
+}
+
+// ------------------------------------------------- SpMSpV: heavy rows (CSR) --
+// One warp per row: the index stream is read 32 wide (coalesced), the gathers are
+// 32 in flight, process_message runs on all lanes.  The fold of each batch is
+//   REORDER = false: lane 0 walks the batch left to right (exact serial order)
+//   REORDER = true : order-preserving pairwise tree (program declared associative)
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool REORDER>
+__global__ void __launch_bounds__(128)
+    k_heavy(prog_bytes<P> pb, gm_matrix_view M, const T* __restrict__ x, const unsigned* __restrict__ xbits,
+            const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  U* buf = reinterpret_cast<U*>(smem) + wib * 32;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int* __restrict__ cols = M.h_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
+
+  for (int slot = warp; slot < M.n_heavy; slot += nwarps) {
+    const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
+    if (beg == end) continue;
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    V vprop;
+    if (NEEDVP) vprop = vp[vtx];
+    U acc;
+    bool have = false;  // meaningful on lane 0
+    if (ACCUM && lane == 0) {
+      have = test_bit(ybits, vtx);
+      if (have) acc = y[vtx];
+    }
+    for (long long k = beg; k < end; k += 32) {
+      const long long idx = k + lane;
+      bool on = idx < end;
+      int c = 0;
+      if (on) {
+        c = __ldg(cols + idx);
+        if (!ALLACT) on = test_bit(xbits, c);
+      }
+      if (on) {
+        T xv = x[c];
+        E ev = vals[idx];
+        U tmp;
+        prog.P::process_message(xv, ev, vprop, tmp);
+        buf[lane] = tmp;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, on);
+      if (m == 0) continue;
+      __syncwarp();
+      if (REORDER) {
+        // order-preserving pairwise tree: at stride d the lane with lane % 2d == 0
+        // absorbs lane + d (left operand first); validity rides along in `v`
+        bool v = on;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned vm = __ballot_sync(0xffffffffu, v);
+          if ((lane & (2 * d - 1)) == 0 && ((vm >> (lane + d)) & 1u)) {
+            if (v) {
+              U a = buf[lane];
+              prog.P::reduce_function(a, buf[lane + d]);
+              buf[lane] = a;
+            } else {
+              buf[lane] = buf[lane + d];
+              v = true;
+            }
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          if (have) prog.P::reduce_function(acc, buf[0]);
+          else { acc = buf[0]; have = true; }
+        }
+      } else {
+        if (lane == 0) {
+          unsigned mm = m;
+          while (mm) {
+            int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            if (have) prog.P::reduce_function(acc, buf[b]);
+            else { acc = buf[b]; have = true; }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && have) {
+      y[vtx] = acc;
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ driver --
+#define GM_CUDA_OK(call)                                                                      \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      fprintf(stderr, "graphmat_b200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), \
+              __FILE__, __LINE__);                                                            \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+struct step_counters {
+  long long launches = 0;
+  long long edges = 0;
+};
+
+template <class P>
+struct engine {
+  typedef decltype(deduce_types((P*)nullptr)) types;
+  typedef typename types::Tm T;
+  typedef typename types::Um U;
+  typedef typename types::Vp V;
+  typedef typename types::Ev E;
+  static constexpr bool REORDER = is_reorderable<P>::value;
+
+  static int check(const gm_graph_view& gv, const gm_vectors_view& vv) {
+    if ((int)sizeof(V) != gv.sizeof_V || (int)sizeof(E) != gv.sizeof_E || (int)sizeof(T) != vv.sizeof_T ||
+        (int)sizeof(U) != vv.sizeof_U) {
+      fprintf(stderr, "graphmat_b200: type sizes do not match the graph/vectors (V %zu/%d E %zu/%d T %zu/%d U %zu/%d)\n",
+              sizeof(V), gv.sizeof_V, sizeof(E), gv.sizeof_E, sizeof(T), vv.sizeof_T, sizeof(U), vv.sizeof_U);
+      return 1;
+    }
+    return 0;
+  }
+
+  // IntersectReduce(active, vertexproperty, &x, send_message)   GraphMatRuntime.h:145
+  static int send(const P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc) {
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    const int n = gv.n_local_pad;
+    T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
+    unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
+    k_send<P, T, V><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), n, (const V*)gv.vertexproperty, gv.active_bits, xloc, xb);
+    if (sc) sc->launches++;
+    GM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+  static int mult_t(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
+                    step_counters* sc) {
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    const T* x = (const T*)vv.x_val;
+    const V* vp = (const V*)gv.vertexproperty;
+    U* y = (U*)vv.y_val;
+    prog_bytes<P> pb = pack(prog);
+    if (M.n_heavy > 0) {
+      int warps = M.n_heavy;
+      int blocks = (warps + 3) / 4;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      size_t sh = 4 * 32 * sizeof(U);
+      k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, x, vv.x_bits, vp, y, vv.y_bits);
+      if (sc) sc->launches++;
+    }
+    if (M.n_slices > 0) {
+      int blocks = (M.n_slices + 7) / 8;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, M, x, vv.x_bits, vp, y, vv.y_bits);
+      if (sc) sc->launches++;
+    }
+    if (sc) sc->edges += M.nnz;
+    GM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  // mult_segment / mult_segment3 for one operand matrix   SPMV.h:62-95
+  static int mult(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
+                  bool allact, bool accum, step_counters* sc) {
+    const bool needvp = prog.getProcessMessageRequiresVertexprop();
+    const bool ident = M.identity != 0;
+#define GM_MULT(A_, N_, I_, C_) return mult_t<A_, N_, I_, C_>(prog, gv, M, vv, sc)
+#define GM_MULT_C(A_, N_, I_) \
+  do { if (accum) GM_MULT(A_, N_, I_, true); else GM_MULT(A_, N_, I_, false); } while (0)
+#define GM_MULT_I(A_, N_) \
+  do { if (ident) GM_MULT_C(A_, N_, true); else GM_MULT_C(A_, N_, false); } while (0)
+#define GM_MULT_N(A_) \
+  do { if (needvp) GM_MULT_I(A_, true); else GM_MULT_I(A_, false); } while (0)
+    if (allact) GM_MULT_N(true);
+    else GM_MULT_N(false);
+#undef GM_MULT
+#undef GM_MULT_C
+#undef GM_MULT_I
+#undef GM_MULT_N
+    return 0;
+  }
+
+  // SpMTSpV / SpMSpV selection   GraphMatRuntime.h:160-176
+  static int spmspv(const P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, bool allact, step_counters* sc) {
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
+    const int order = (int)prog.getOrder();
+    if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc);
+    if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc);
+    if (order == GraphMat::ALL_EDGES) {
+      if (mult(prog, gv, gv.AT, vv, allact, false, sc)) return 1;
+      return mult(prog, gv, gv.A, vv, allact, true, sc);
+    }
+    printf("Unrecognized option \n");
+    exit(1);
+  }
+
+  // the apply loop   GraphMatRuntime.h:184-226 (flag = !converged)
+  static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc) {
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    const int n = gv.n_local_pad;
+    k_apply<P, U, V><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), n, (const U*)vv.y_val, vv.y_bits, (V*)gv.vertexproperty,
+                                                     gv.active_bits, gv.d_flags);
+    if (sc) sc->launches++;
+    GM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  static int set_all_active(const gm_graph_view& gv, step_counters* sc) {
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    int words = gv.n_local_pad >> 5;
+    k_fill_bits<<<(words + 255) / 256, 256, 0, st>>>(gv.active_bits, gv.n_local, gv.n_local_pad);
+    if (sc) sc->launches++;
+    GM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  // run_graph_program   GraphMatRuntime.h:93-279
+  static int run(P& prog, gm_graph* g, int iterations, gm_vectors* tmp, gm_run_stats* stats) {
+    gm_graph_view gv;
+    if (gm_graph_view_get(g, &gv)) return 1;
+    gm_vectors* own = nullptr;
+    if (!tmp) {
+      if (gm_vectors_create(&own, g, (int)sizeof(T), (int)sizeof(U))) return 1;
+      tmp = own;
+    }
+    gm_vectors_view vv;
+    if (gm_vectors_view_get(tmp, &vv)) return 1;
+    if (check(gv, vv)) return 1;
+    cudaStream_t st = (cudaStream_t)gv.stream;
+    step_counters sc;
+    cudaEvent_t e0, e1, s0, s1;
+    GM_CUDA_OK(cudaEventCreate(&e0));
+    GM_CUDA_OK(cudaEventCreate(&e1));
+    GM_CUDA_OK(cudaEventCreate(&s0));
+    GM_CUDA_OK(cudaEventCreate(&s1));
+    float ms_spmv = 0.f;
+    const bool all = prog.getActivity() == GraphMat::ALL_VERTICES;
+    GM_CUDA_OK(cudaEventRecord(e0, st));
+    if (all && set_all_active(gv, &sc)) return 1;
+    int it = 0, converged = 1;
+    while (1) {
+      GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
+      if (send(prog, gv, vv, &sc)) return 1;
+      if (gv.world > 1 && gm_graph_exchange_x(g, tmp)) return 1;
+      const bool timing = stats != nullptr;
+      if (timing) GM_CUDA_OK(cudaEventRecord(s0, st));
+      if (spmspv(prog, gv, vv, all, &sc)) return 1;
+      if (timing) GM_CUDA_OK(cudaEventRecord(s1, st));
+      if (apply(prog, gv, vv, &sc)) return 1;
+      GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GM_CUDA_OK(cudaStreamSynchronize(st));
+      int changed = gv.h_flags[0];
+      if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
+      converged = !changed;
+      if (timing) {
+        float t;
+        GM_CUDA_OK(cudaEventElapsedTime(&t, s0, s1));
+        ms_spmv += t;
+      }
+      prog.do_every_iteration(it);
+      if (all && set_all_active(gv, &sc)) return 1;
+      it++;
+      if (it == iterations) break;
+      if (iterations <= 0 && converged) break;
+    }
+    GM_CUDA_OK(cudaEventRecord(e1, st));
+    GM_CUDA_OK(cudaEventSynchronize(e1));
+    if (stats) {
+      float t;
+      GM_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+      stats->iterations = it;
+      stats->converged = converged;
+      stats->ms_total = t;
+      stats->ms_spmv = ms_spmv;
+      stats->kernel_launches = sc.launches;
+      stats->edges_processed = sc.edges;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(s0);
+    cudaEventDestroy(s1);
+    if (own) gm_vectors_destroy(own);
+    return 0;
+  }
+};
+
+}  // namespace gm
+#endif

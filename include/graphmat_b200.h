@@ -1,0 +1,177 @@
+/* graphmat_b200.h -- C ABI of the B200-native GraphMat hot path.
+ *
+ * The reference (narayanan2004/GraphMat) has no C ABI: its plugin surface is the
+ * C++ template API (GraphProgram<T,U,V,E>, Graph<V,E>, run_graph_program), which
+ * it lowers internally to C function pointers + void* (include/SPMV.h:41-59,
+ * include/GraphMatRuntime.h:79-91, include/GMDP/multinode/spmspv.h:43-44).  This
+ * header is the boundary a maintainer would bind instead of those internals; each
+ * entry cites the reference interface it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only; all status returns are
+ * 0 = ok, non-zero = error (text via gm_last_error()).  The reference's own
+ * convention is printf + exit(1) (include/GraphProgram.h:73-96); the C++ mirror
+ * in graphmat_b200/include keeps that behaviour on top of these status codes.
+ *
+ * Vertex ids at this boundary are the reference's PUBLIC ids: 1-based, before
+ * Graph::vertexToNative (include/Graph.h:111-130).
+ */
+#ifndef GRAPHMAT_B200_H
+#define GRAPHMAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gm_graph gm_graph;     /* replaces GraphMat::Graph<V,E> (include/Graph.h:58-107) */
+typedef struct gm_vectors gm_vectors; /* replaces run_graph_program_temp_structure (include/GraphMatRuntime.h:53-57) */
+
+/* include/GraphProgram.h:34,36 */
+enum { GM_OUT_EDGES = 0, GM_IN_EDGES = 1, GM_ALL_EDGES = 2 };
+enum { GM_ACTIVE_ONLY = 0, GM_ALL_VERTICES = 1 };
+#define GM_UNTIL_CONVERGENCE (-1) /* include/GraphMatRuntime.h:51 */
+
+/* Layout options.  ref_threads reproduces the reference's thread-count dependent
+ * vertex permutation (include/Graph.h:117: npartitions = num_threads*16*nranks),
+ * which fixes the per-row fold order; results equal a 1-rank reference run with
+ * OMP_NUM_THREADS == ref_threads whatever (rank, world) the rows are sharded on. */
+typedef struct gm_graph_opts {
+  int ref_threads;      /* default 4 when 0 */
+  int rank, world;      /* tile-row sharding: this process owns 1/world of the rows; default 0,1 */
+  int heavy_threshold;  /* rows longer than this use the row-cooperative kernel; 0 = default */
+  int edges_on_device;  /* src/dst/val are device pointers */
+  const gm_graph* order_like; /* adopt this graph's vertex placement (needed before gm_graph_share_vertexproperty) */
+  int build_mask;       /* bit0: A (IN_EDGES operand), bit1: AT (OUT_EDGES operand); 0 = both (include/Graph.h:226-227) */
+} gm_graph_opts;
+
+/* One operand matrix as the kernels see it (device pointers).  Rows ("slots") are
+ * sorted by decreasing length; the first n_heavy rows are stored row-contiguous
+ * (CSR), the rest as 32-row sliced-ELL.  Within a row entries are in ascending
+ * NATIVE column id -- the reference's fold order (include/GMDP/singlenode/spmspv.h:55-77). */
+typedef struct gm_matrix_view {
+  int n_slots, n_heavy, n_slices, identity;
+  const int* slot_vertex;       /* slot -> local vertex (unused when identity) */
+  const int* row_len;           /* n_slots */
+  const long long* h_ptr;       /* n_heavy + 1 */
+  const int* h_col;             /* x index per entry */
+  const void* h_val;            /* edge value per entry */
+  const long long* slice_ptr;   /* n_slices + 1, entry offsets (32 * width each) */
+  const int* s_col;
+  const void* s_val;
+  long long nnz;                /* entries owned by this rank */
+} gm_matrix_view;
+
+typedef struct gm_graph_view {
+  int nvertices, n_local, n_local_pad, n_full, rank, world, ref_threads;
+  int sizeof_V, sizeof_E;
+  long long nnz;                /* whole graph */
+  void* vertexproperty;         /* device, n_local_pad * sizeof_V (include/Graph.h:70) */
+  unsigned int* active_bits;    /* device, n_local_pad / 32 words (include/Graph.h:71) */
+  gm_matrix_view A, AT;         /* include/Graph.h:68-69 */
+  int* d_flags;                 /* device scratch: [0] = "some vertex changed" */
+  int* h_flags;                 /* pinned host mirror */
+  void* stream;                 /* cudaStream_t all work is ordered on */
+} gm_graph_view;
+
+typedef struct gm_vectors_view {
+  int sizeof_T, sizeof_U;
+  void* x_val; unsigned int* x_bits;  /* n_full entries: the all-gathered message vector */
+  void* y_val; unsigned int* y_bits;  /* n_local_pad entries */
+} gm_vectors_view;
+
+typedef struct gm_run_stats {
+  int iterations;        /* iterations executed ("Completed %d iterations", GraphMatRuntime.h:277) */
+  int converged;
+  float ms_total;        /* device time of the whole call (CUDA events) */
+  float ms_spmv;         /* device time inside the SpMSpV kernels */
+  long long kernel_launches;
+  long long edges_processed; /* matrix entries swept */
+} gm_run_stats;
+
+const char* gm_last_error(void);
+int gm_set_device(int device);
+int gm_device_count(void);
+
+/* ---- graph: replaces Graph::ReadEdgelist / ReadMTX (include/Graph.h:210-260) ---- */
+/* src/dst: nnz public 1-based ids; val: nnz edge values of sizeof_E bytes (NULL = all-ones int);
+ * nvertices = max(m, n) (the squaring of Graph.h:253-257 is the caller's job). */
+int gm_graph_create(gm_graph** out, int nvertices, long long nnz, const int* src, const int* dst, const void* val,
+                    int sizeof_E, int sizeof_V, const gm_graph_opts* opts);
+/* Synthetic RMAT (a,b,c = .57,.19,.19, duplicates and self loops kept) generated on the device;
+ * weight_max == 0 -> all weights 1, else uniform int in [1, weight_max]. */
+int gm_graph_create_rmat(gm_graph** out, int scale, int edge_factor, unsigned long long seed, int weight_max,
+                         unsigned long long weight_seed, int sizeof_V, const gm_graph_opts* opts);
+/* the same generator on the host (no GPU needed): fills nnz = edge_factor << scale edges, public ids */
+int gm_rmat_edges_host(int scale, int edge_factor, unsigned long long seed, int weight_max,
+                       unsigned long long weight_seed, int* src, int* dst, int* val);
+int gm_graph_destroy(gm_graph* g);
+int gm_graph_view_get(const gm_graph* g, gm_graph_view* out);
+int gm_graph_synchronize(const gm_graph* g);
+
+/* include/Graph.h:263-292 */
+int gm_graph_set_all_active(gm_graph* g);
+int gm_graph_set_all_inactive(gm_graph* g);
+int gm_graph_set_active(gm_graph* g, int v);
+int gm_graph_set_inactive(gm_graph* g, int v);
+/* include/Graph.h:300-364; values are sizeof_V bytes each, arrays are in public-id order (index v-1) */
+int gm_graph_set_all_vertexproperty(gm_graph* g, const void* value);
+int gm_graph_set_vertexproperty(gm_graph* g, int v, const void* value);
+int gm_graph_get_vertexproperty(const gm_graph* g, int v, void* value);
+int gm_graph_set_vertexproperties(gm_graph* g, const void* values);   /* whole array, host */
+int gm_graph_get_vertexproperties(const gm_graph* g, void* values);   /* whole array, host; on world>1 only owned entries are written */
+int gm_graph_share_vertexproperty(gm_graph* g, gm_graph* owner);      /* g must have been created order_like = owner */
+int gm_graph_vertex_owner(const gm_graph* g, int v);                  /* Graph::vertexNodeOwner, returns owning rank */
+int gm_graph_out_degree_source(const gm_graph* g, int* v);            /* first public id with an out-edge (bench source) */
+
+/* ---- x / y: graph_program_init / graph_program_clear (include/GraphMatRuntime.h:59-76) ---- */
+int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int sizeof_U);
+int gm_vectors_destroy(gm_vectors* v);
+int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* out);
+
+/* ---- multi-GPU exchange (replaces the MPI sends of include/GMDP/multinode/spmspv.h:61-116 and the
+ *      Allreduce of include/GraphMatRuntime.h:226).  The library calls these between send and SpMSpV /
+ *      after apply when world > 1; the host language supplies them (NCCL through torch.distributed, MPI, ...). */
+typedef int (*gm_allgather_fn)(void* ctx, void* buf, long long bytes_per_rank, void* stream);
+typedef int (*gm_allreduce_or_fn)(void* ctx, int* host_flag);
+int gm_graph_set_exchange(gm_graph* g, gm_allgather_fn allgather, gm_allreduce_or_fn allreduce_or, void* ctx);
+int gm_graph_exchange_x(gm_graph* g, gm_vectors* v);     /* all-gather x values + bit words in place */
+int gm_graph_allreduce_or(gm_graph* g, int* flag);       /* "some vertex changed" across ranks */
+
+/* ---- the five vertex programs BASELINE.json names, compiled into the library ----
+ * run == run_graph_program(&program, G, iterations, &tmp) (include/GraphMatRuntime.h:93-279).
+ * `state` is the program's own state block, read and written back (do_every_iteration mutates it). */
+enum {
+  GM_PROG_DEGREE = 1,        /* src/PageRank.cpp:54-79   V = PR                 */
+  GM_PROG_PAGERANK = 2,      /* src/PageRank.cpp:81-112  V = PR                 */
+  GM_PROG_BFS = 3,           /* src/BFS.cpp:61-99        V = BFSD2              */
+  GM_PROG_SSSP = 4,          /* src/SSSP.cpp:62-90       V = SSSP_vertex_type   */
+  GM_PROG_DELTASTEPPING = 5, /* src/DeltaStepping.cpp:64-98 V = DeltaSteppingDS */
+  GM_PROG_SGD20 = 6,         /* src/SGD.cpp:77-121 K=20  V = LatentVector<20>   */
+  GM_PROG_RMSE20 = 7,        /* src/SGD.cpp:123-156 K=20                        */
+  GM_PROG_SGD32 = 8,
+  GM_PROG_RMSE32 = 9,
+  GM_PROG_SGD4 = 10,
+  GM_PROG_RMSE4 = 11
+};
+typedef struct gm_pagerank_state { float alpha; } gm_pagerank_state;                  /* src/PageRank.cpp:84 */
+typedef struct gm_bfs_state { unsigned int current_depth; } gm_bfs_state;             /* src/BFS.cpp:64 */
+typedef struct gm_deltastepping_state { int delta, bid; } gm_deltastepping_state;     /* src/DeltaStepping.cpp:67-68 */
+typedef struct gm_sgd_state { double lambda, step; } gm_sgd_state;                    /* src/SGD.cpp:79-80 */
+
+int gm_program_sizes(int program, int* sizeof_T, int* sizeof_U, int* sizeof_V, int* sizeof_state);
+int gm_run_program(gm_graph* g, int program, void* state, int iterations, gm_vectors* tmp, gm_run_stats* stats);
+/* the three steps of one iteration, separately (tests; include/GraphMatRuntime.h:145,160-176,184-226) */
+int gm_step_send(gm_graph* g, int program, const void* state, gm_vectors* tmp);
+int gm_step_spmspv(gm_graph* g, int program, const void* state, gm_vectors* tmp);
+int gm_step_apply(gm_graph* g, int program, void* state, gm_vectors* tmp, int* changed);
+
+/* Graph::applyReduceAllVertices (include/Graph.h:377-381) for the app drivers' three map functions */
+enum { GM_REDUCE_REACHABLE = 1,      /* src/BFS.cpp:101-108 etc.: count of vertices whose first uint field < UINT_MAX */
+       GM_REDUCE_BUCKET_NOT_EMPTY = 2, /* src/DeltaStepping.cpp:109-111, param = bid */
+       GM_REDUCE_SQERR = 3 };        /* src/SGD.cpp:158-161: sum of the trailing double (sqerr) */
+int gm_graph_reduce(const gm_graph* g, int what, int param, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

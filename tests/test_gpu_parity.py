@@ -1,0 +1,208 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  * the committed golden vectors of the unmodified reference (tests/golden),
+  * the C oracle (oracle/gm_oracle.c) on the same seeded inputs,
+  * size-independent properties at larger sizes.
+Bars: bit-exact for BFS depth/parent, SSSP/DeltaStepping distance/bucket, degrees and
+iteration counts; PageRank and SGD within 1e-6 relative (north_star) -- PageRank is in
+fact compared bit-for-bit because the engine keeps the reference's fold order.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from graphmat_b200 import apps, capi
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+G = util.GOLDEN
+REL = 1e-6  # north_star tolerance for floating-point programs
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def assert_rel(a, b, rel=REL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    assert err.max() <= rel, "max relative error %g" % err.max()
+
+
+@pytest.mark.parametrize("t", [1, 2, 4])
+def test_golden_test_mtx(t):
+    g = load("test_mtx_t%d" % t)
+    m = util.TEST_MTX
+    pr, deg, it = apps.pagerank(m["n"], m["src"], m["dst"], m["val"], threads=t)
+    assert it == int(g["pr_iterations"]) and (deg == g["degree"]).all()
+    assert_rel(pr, g["pagerank"])
+    depth, parent, bit, reach = apps.bfs(m["n"], m["src"], m["dst"], 1, m["val"], threads=t)
+    assert (depth == g["depth"]).all() and (parent == g["parent"]).all()
+    assert bit == int(g["bfs_iterations"]) and reach == int(g["reachable"])
+    dist, sit, _ = apps.sssp(m["n"], m["src"], m["dst"], m["val"], 1, threads=t)
+    assert (dist == g["sssp_distance"]).all() and sit == int(g["sssp_iterations"])
+    ddist, dbucket, nb, _ = apps.deltastepping(m["n"], m["src"], m["dst"], m["val"], 2, 1, threads=t)
+    assert (ddist == g["ds_distance"]).all() and (dbucket == g["ds_bucket"]).all() and nb == int(g["ds_buckets"])
+
+
+def test_golden_ratings7():
+    g = load("ratings7_t4")
+    r = util.RATINGS7
+    lv, r0, r1 = apps.sgd(r["m"], r["n"], r["src"], r["dst"], r["val"], K=20, threads=4)
+    assert_rel(lv, g["lv"])
+    assert_rel([r0, r1], [g["rmse0"], g["rmse1"]])
+
+
+def test_golden_upper_triangle():
+    g = load("upper_triangle_t4")
+    n = int(g["n"])
+    depth, parent, bit, reach = apps.bfs(n, g["src"], g["dst"], 1, g["val"], threads=4)
+    assert (depth == g["depth"]).all() and (parent == g["parent"]).all()
+    assert bit == int(g["bfs_iterations"]) and reach == int(g["reachable"])
+    dist, sit, _ = apps.sssp(n, g["src"], g["dst"], g["val"], 1, threads=4)
+    assert (dist == g["sssp_distance"]).all() and sit == int(g["sssp_iterations"])
+
+
+@pytest.mark.parametrize("t", [1, 4])
+@pytest.mark.parametrize("heavy", [0, 16])  # 16: push most rows through the row-cooperative kernel
+def test_golden_rmat12(t, heavy):
+    g = load("rmat12_t%d" % t)
+    n, s, d, v = util.rmat_numpy(12, weight_max=127)
+    src0 = int(g["source"])
+    kw = dict(threads=t, heavy_threshold=heavy)
+    pr, deg, it = apps.pagerank(n, s, d, None, **kw)
+    assert it == int(g["pr_iterations"]) and (deg == g["degree"]).all()
+    assert_rel(pr, g["pagerank"])
+    assert (pr == g["pagerank"]).all(), "PageRank is expected bit-identical (same fold order)"
+    pr10, _, _ = apps.pagerank(n, s, d, None, iterations=10, **kw)
+    assert (pr10 == g["pagerank10"]).all()
+    depth, parent, bit, reach = apps.bfs(n, s, d, src0, None, **kw)
+    assert (depth == g["depth"]).all() and (parent == g["parent"]).all() and bit == int(g["bfs_iterations"])
+    dist, sit, _ = apps.sssp(n, s, d, v, src0, **kw)
+    assert (dist == g["sssp_distance"]).all() and sit == int(g["sssp_iterations"])
+    ddist, dbucket, nb, _ = apps.deltastepping(n, s, d, v, 16, src0, **kw)
+    assert (ddist == g["ds_distance"]).all() and (dbucket == g["ds_bucket"]).all() and nb == int(g["ds_buckets"])
+
+
+@pytest.mark.parametrize("K", [20, 32])
+def test_golden_ratings(K):
+    g = load("ratings_k%d_t4" % K)
+    u, it_, r_ = util.ratings(300, 60, 4000)
+    lv, r0, r1 = apps.sgd(300, 360, u, it_, r_, K=K, threads=4)
+    assert_rel(lv, g["lv"])
+    assert_rel([r0, r1], [g["rmse0"], g["rmse1"]])
+
+
+@pytest.mark.parametrize("n", [100, 500])
+@pytest.mark.parametrize("start", ["first", "mid"])
+def test_bfs_closed_forms(n, start):
+    """the reference's own BFS tests (test/test_bfs.cpp:97-258)"""
+    s0 = 1 if start == "first" else n // 2
+    s, d = util.upper_triangular(n)
+    depth, _, _, _ = apps.bfs(n, s, d, s0, threads=4)
+    exp = np.where(np.arange(1, n + 1) > s0, 1, 0xFFFFFFFF).astype(np.uint32)
+    exp[s0 - 1] = 0
+    assert (depth == exp).all()
+    s, d = util.dense(n)
+    depth, _, _, _ = apps.bfs(n, s, d, s0, threads=4)
+    assert depth[s0 - 1] == 0 and (np.delete(depth, s0 - 1) == 1).all()
+    s, d = util.circular_chain(n)
+    depth, _, _, _ = apps.bfs(n, s, d, s0, threads=4)
+    assert (depth == (np.arange(1, n + 1) - s0) % n).all()
+
+
+@pytest.mark.parametrize("seed,t,n,m", [(21, 1, 700, 9000), (22, 2, 1000, 40000), (23, 4, 5000, 30000),
+                                        (24, 3, 33, 400), (25, 8, 4096, 100000)])
+def test_vs_oracle_random(seed, t, n, m):
+    s, d, v = util.random_graph(n, m, seed, weight_max=50)
+    src0 = util.first_source(s)
+    a = apps.pagerank(n, s, d, None, threads=t)
+    b = port.pagerank(n, s, d, None, threads=t)
+    assert a[2] == b[2] and (a[1] == b[1]).all()
+    assert_rel(a[0], b[0])
+    a = apps.bfs(n, s, d, src0, threads=t)
+    b = port.bfs(n, s, d, src0, threads=t)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2] and a[3] == b[3]
+    a = apps.sssp(n, s, d, v, src0, threads=t)
+    b = port.sssp(n, s, d, v, src0, threads=t)
+    assert (a[0] == b[0]).all() and a[1] == b[1] and a[2] == b[2]
+    a = apps.deltastepping(n, s, d, v, 10, src0, threads=t)
+    b = port.deltastepping(n, s, d, v, 10, src0, threads=t)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2]
+
+
+def test_vs_oracle_rmat16_library_generator():
+    """the library's own RMAT generator (device) and its host twin produce the same graph"""
+    n, s, d, v = capi.rmat_edges(16, 16, seed=1)
+    Gd = capi.Graph.rmat(16, capi.PR_DTYPE, seed=1, threads=4)
+    a = apps.pagerank(n, None, None, graph=Gd, iterations=10)
+    b = port.pagerank(n, s, d, None, threads=4, iterations=10)
+    assert (a[1] == b[1]).all()
+    assert_rel(a[0], b[0])
+    assert (a[0] == b[0]).all()
+    src0 = util.first_source(s)
+    assert Gd.first_source() == src0
+    Gb = capi.Graph.rmat(16, capi.BFS_DTYPE, seed=1, threads=4)
+    a = apps.bfs(n, None, None, src0, graph=Gb)
+    b = port.bfs(n, s, d, src0, threads=4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2] and a[3] == b[3]
+
+
+def test_sgd_vs_oracle():
+    u, it_, r_ = util.ratings(500, 100, 20000, seed=9)
+    a = apps.sgd(500, 600, u, it_, r_, K=20, threads=4)
+    b = port.sgd(500, 600, u, it_, r_, K=20, threads=4)
+    assert_rel(a[0], b[0])
+    assert_rel(a[1:], b[1:])
+
+
+def test_empty_and_edge_cases():
+    e = np.array([], np.int32)
+    pr, deg, it = apps.pagerank(40, e, e, None, threads=1)
+    assert it == 1 and (deg == 0).all() and np.allclose(pr, 0.3)
+    depth, parent, bit, reach = apps.bfs(40, np.array([2], np.int32), np.array([3], np.int32), 1, threads=1)
+    assert reach == 1 and bit == 1 and depth[0] == 0
+    # thread-count dependent parent (SURVEY.md hazard 2)
+    s = np.array([1, 1, 2, 17], np.int32)
+    d = np.array([2, 17, 3, 3], np.int32)
+    assert apps.bfs(64, s, d, 1, threads=1)[1][2] == 2
+    assert apps.bfs(64, s, d, 1, threads=2)[1][2] == 17
+    # single-vertex accessors go through the id permutation (test/test_graph_basics.cpp:56-145)
+    Gr = capi.Graph.from_edges(100, s, d, None, capi.SSSP_DTYPE, threads=2)
+    for v in (1, 2, 50, 100):
+        Gr.set_vertexproperty(v, (v * 7,))
+    for v in (1, 2, 50, 100):
+        assert Gr.get_vertexproperty(v)["distance"] == v * 7
+    allv = Gr.get_vertexproperties()
+    assert allv["distance"][49] == 350 and allv["distance"][0] == 7
+
+
+def test_properties_at_scale():
+    """RMAT-20 (16.8 M edges): size-independent checks instead of the oracle."""
+    Gd = capi.Graph.rmat(20, capi.PR_DTYPE, seed=1, threads=4)
+    n = Gd.nvertices
+    pr, deg, it = apps.pagerank(n, None, None, graph=Gd, iterations=3)
+    _, s, d, _ = capi.rmat_edges(20, 16, seed=1)
+    assert (deg == np.bincount(s - 1, minlength=n)).all()          # Degree pass == out-degree histogram
+    indeg = np.bincount(d - 1, minlength=n)
+    assert (pr[indeg == 0] == np.float32(0.3)).all()                # apply only where a message arrived
+    assert np.isfinite(pr).all() and (pr >= np.float32(0.3) - 1e-6).all()
+    src0 = util.first_source(s)
+    Gb = capi.Graph.rmat(20, capi.BFS_DTYPE, seed=1, threads=4)
+    depth, parent, bit, reach = apps.bfs(n, None, None, src0, graph=Gb)
+    vis = depth < 0xFFFFFFFF
+    assert reach == vis.sum() and depth[src0 - 1] == 0
+    # every visited non-source vertex has a visited parent exactly one level up, and (parent, v) is an edge
+    idx = np.nonzero(vis)[0]
+    idx = idx[idx != src0 - 1]
+    p = parent[idx].astype(np.int64)
+    assert (depth[p - 1] + 1 == depth[idx]).all()
+    edges = set(zip(s.tolist(), d.tolist())) if n <= (1 << 16) else None
+    key = s.astype(np.int64) * (n + 1) + d
+    key.sort()
+    q = p * (n + 1) + (idx + 1)
+    pos = np.searchsorted(key, q)
+    assert (key[np.minimum(pos, len(key) - 1)] == q).all()
+    # no edge skips a level
+    assert (depth[d - 1][vis[s - 1]] <= depth[s - 1][vis[s - 1]] + 1).all()
