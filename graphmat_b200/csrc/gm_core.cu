@@ -223,6 +223,13 @@ extern "C" int gm_device_count(void) {
   return n;
 }
 
+// blocking device->host read ordered on the graph's (non-blocking) stream
+static int d2h(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 static inline unsigned nblk(long long n, int b = 256) { return (unsigned)((n + b - 1) / b); }
 
 static int ceil_log2(long long v) {
@@ -320,7 +327,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   k_len_to_ll<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, len_ll, 1);
   if (exclusive_scan_ll(len_ll, row_ptr, n_pad, st)) return 1;
   long long owned = 0;
-  CK(cudaMemcpy(&owned, row_ptr + n_pad, 8, cudaMemcpyDeviceToHost));
+  if (d2h(&owned, row_ptr + n_pad, 8, st)) return 1;
   M.nnz = owned;
 
   // heavy prefix / non-empty prefix
@@ -330,7 +337,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, g->heavy_threshold, cnt);
   k_count_nonzero<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, cnt + 1);
   int hc[2];
-  CK(cudaMemcpy(hc, cnt, 8, cudaMemcpyDeviceToHost));
+  if (d2h(hc, cnt, 8, st)) return 1;
   cudaFree(cnt);
   int n_heavy = std::min(n_pad, (hc[0] + 31) / 32 * 32);
   int n_nonzero = hc[1];
@@ -355,7 +362,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   long long nh = 0;
   if (dalloc(&M.h_ptr, (size_t)n_heavy + 1)) return 1;
   CK(cudaMemcpyAsync(M.h_ptr, row_ptr, ((size_t)n_heavy + 1) * 8, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpy(&nh, row_ptr + n_heavy, 8, cudaMemcpyDeviceToHost));
+  if (d2h(&nh, row_ptr + n_heavy, 8, st)) return 1;
   E* hv = nullptr;
   if (dalloc(&M.h_col, nh) || dalloc(&hv, nh)) return 1;
   M.h_val = hv;
@@ -368,7 +375,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   if (n_slices) k_slice_width<<<nblk(n_slices), 256, 0, st>>>(M.row_len, n_heavy, n_slices, widths);
   if (exclusive_scan_ll(widths, M.slice_ptr, n_slices, st)) return 1;
   long long total = 0;
-  CK(cudaMemcpy(&total, M.slice_ptr + n_slices, 8, cudaMemcpyDeviceToHost));
+  if (d2h(&total, M.slice_ptr + n_slices, 8, st)) return 1;
   E* sv = nullptr;
   if (dalloc(&M.s_col, total) || dalloc(&sv, total)) return 1;
   M.s_val = sv;
@@ -425,7 +432,7 @@ static int build_graph(gm_graph* g, int* d_src, int* d_dst, const E* d_val, long
     void* tmp;
     CK(cudaMalloc(&tmp, tb ? tb : 1));
     CK(cub::DeviceReduce::Min(tmp, tb, d_src, dmin, nnz, st));
-    CK(cudaMemcpy(&g->first_source, dmin, 4, cudaMemcpyDeviceToHost));
+    if (d2h(&g->first_source, dmin, 4, st)) return 1;
     cudaFree(tmp);
     cudaFree(dmin);
     k_to_native<<<nblk(nnz), 256, 0, st>>>(d_src, nnz, n, npart);
@@ -623,7 +630,7 @@ static int host_xidx(const gm_graph* g) {
   gm_graph* m = const_cast<gm_graph*>(g);
   if (m->h_xidx.empty()) {
     m->h_xidx.resize(g->n);
-    CK(cudaMemcpy(m->h_xidx.data(), g->d_xidx, (size_t)g->n * 4, cudaMemcpyDeviceToHost));
+    if (d2h(m->h_xidx.data(), g->d_xidx, (size_t)g->n * 4, g->stream)) return 1;
   }
   return 0;
 }

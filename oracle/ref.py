@@ -101,3 +101,28 @@ def sgd(m, n, src, dst, val, K=20, iterations=10, lam=0.001, step=0.00000035, th
     if r < 0:
         raise ValueError("reference SGD built for K in {4, 20, 32}")
     return lv, rmse[0], rmse[1], ms.value
+
+
+class PageRankSession:
+    """Build once, time run_graph_program per call (bench.py reference arm / cpu_baseline)."""
+
+    def __init__(self, n, src, dst, val=None, threads=4):
+        src, dst = _i32(src), _i32(dst)
+        val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+        L = _lib("pagerank")
+        L.gm_ref_pagerank_open.restype = C.c_void_p
+        self.threads = threads
+        self.nnz = len(src)
+        self.h = C.c_void_p(L.gm_ref_pagerank_open(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src),
+                                                   _p(dst), _p(val)))
+
+    def run(self, iterations):
+        """-> (iterations run, ms of run_graph_program)"""
+        ms = C.c_double()
+        it = _lib("pagerank").gm_ref_pagerank_run(self.h, C.c_int(self.threads), C.c_int(iterations), C.byref(ms))
+        return it, ms.value
+
+    def close(self):
+        if self.h:
+            _lib("pagerank").gm_ref_pagerank_close(self.h)
+            self.h = None
