@@ -34,7 +34,7 @@ def latent_dtype(K):
 
 class GraphOpts(C.Structure):
     _fields_ = [("ref_threads", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("heavy_threshold", C.c_int),
-                ("edges_on_device", C.c_int), ("order_like", C.c_void_p), ("build_mask", C.c_int)]
+                ("coop_threshold", C.c_int), ("edges_on_device", C.c_int), ("order_like", C.c_void_p), ("build_mask", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -44,7 +44,7 @@ class RunStats(C.Structure):
 
 class MatrixView(C.Structure):
     _fields_ = [("n_slots", C.c_int), ("n_heavy", C.c_int), ("n_slices", C.c_int), ("identity", C.c_int),
-                ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
+                ("n_coop", C.c_int), ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
                 ("nnz", C.c_longlong)]
 
@@ -90,7 +90,8 @@ SYMBOLS = [
     "gm_graph_get_vertexproperties", "gm_graph_share_vertexproperty", "gm_graph_vertex_owner",
     "gm_graph_out_degree_source", "gm_vectors_create", "gm_vectors_destroy", "gm_vectors_view_get",
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
-    "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce",
+    "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
+    "gm_debug_fold_f32_device",
 ]
 
 
@@ -147,9 +148,10 @@ class Graph:
         self._keep = []
 
     @staticmethod
-    def _opts(threads, rank, world, heavy_threshold, order_like, build_mask, on_device=False):
+    def _opts(threads, rank, world, heavy_threshold, order_like, build_mask, on_device=False, coop_threshold=0):
         o = GraphOpts()
         o.ref_threads, o.rank, o.world, o.heavy_threshold = threads, rank, world, heavy_threshold
+        o.coop_threshold = coop_threshold
         o.edges_on_device = 1 if on_device else 0
         o.order_like = order_like.h if order_like is not None else None
         o.build_mask = build_mask
@@ -157,11 +159,11 @@ class Graph:
 
     @classmethod
     def from_edges(cls, n, src, dst, val, vdtype, threads=4, rank=0, world=1, heavy_threshold=0, order_like=None,
-                   build_mask=0):
+                   build_mask=0, coop_threshold=0):
         src, dst = _i32(src), _i32(dst)
         val = _i32(val) if val is not None else None
         h = C.c_void_p()
-        o = cls._opts(threads, rank, world, heavy_threshold, order_like, build_mask)
+        o = cls._opts(threads, rank, world, heavy_threshold, order_like, build_mask, coop_threshold=coop_threshold)
         _check(lib().gm_graph_create(C.byref(h), C.c_int(n), C.c_longlong(len(src)), _p(src), _p(dst),
                                      _p(val) if val is not None else None, C.c_int(4),
                                      C.c_int(np.dtype(vdtype).itemsize), C.byref(o)), "gm_graph_create")
@@ -169,9 +171,9 @@ class Graph:
 
     @classmethod
     def rmat(cls, scale, vdtype, edge_factor=16, seed=1, weight_max=0, weight_seed=2, threads=4, rank=0, world=1,
-             heavy_threshold=0, build_mask=0):
+             heavy_threshold=0, build_mask=0, coop_threshold=0):
         h = C.c_void_p()
-        o = cls._opts(threads, rank, world, heavy_threshold, None, build_mask)
+        o = cls._opts(threads, rank, world, heavy_threshold, None, build_mask, coop_threshold=coop_threshold)
         _check(lib().gm_graph_create_rmat(C.byref(h), C.c_int(scale), C.c_int(edge_factor), C.c_ulonglong(seed),
                                           C.c_int(weight_max), C.c_ulonglong(weight_seed),
                                           C.c_int(np.dtype(vdtype).itemsize), C.byref(o)), "gm_graph_create_rmat")
@@ -300,3 +302,20 @@ class Vectors:
             self.close()
         except Exception:
             pass
+
+
+def fold_f32_host(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = C.c_float()
+    rc = lib().gm_debug_fold_f32_host(_p(a), C.c_longlong(len(a)), C.byref(out))
+    assert rc in (0, 2)
+    return np.float32(out.value)
+
+
+def fold_f32_device(a, warps=1, offset=0):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = C.c_float()
+    rc = lib().gm_debug_fold_f32_device(_p(a), C.c_longlong(len(a)), C.c_int(warps), C.c_int(offset), C.byref(out))
+    if rc not in (0, 2):
+        _check(rc, "gm_debug_fold_f32_device")
+    return np.float32(out.value)

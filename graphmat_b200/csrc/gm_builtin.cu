@@ -151,3 +151,113 @@ extern "C" int gm_step_apply(gm_graph* g, int program, void* state, gm_vectors* 
   call c = {OP_APPLY, g, state, 0, tmp, nullptr, changed, nullptr, nullptr, nullptr, nullptr};
   return route(program, c);
 }
+
+// ---- test hooks for the exact fp32 fold (gm_fadd32.cuh) ----
+namespace {
+// host walk through the same block structure and the same fx:: arithmetic as fx::warp_fold
+void host_warp_fold(const float* v /*256*/, const unsigned* vmask /*32*/, float& s, bool& have) {
+  using namespace gm::fx;
+  unsigned pending = 0;
+  for (int l = 0; l < 32; l++) if (vmask[l]) pending |= 1u << l;
+  while (pending) {
+    binade b;
+    bool hot = have && binade_of(s, b);
+    if (!hot) {
+      int f = __builtin_ctz(pending);
+      float vv[8];
+      for (int k = 0; k < 8; k++) vv[k] = v[f * 8 + k];
+      serial8(vv, vmask[f], s, have);
+      pending &= ~(1u << f);
+      continue;
+    }
+    qmap incl[32];
+    bool over[32];
+    qmap run = identity();
+    for (int l = 0; l < 32; l++) {
+      bool bad = false;
+      qmap mine = identity();
+      if ((pending >> l) & 1u)
+        for (int k = 0; k < 8; k++) mine = compose(mine, quantize(v[l * 8 + k], b, bad));
+      run = compose(run, mine);
+      incl[l] = run;
+      over[l] = bad || apply(run, b.m) >= (1u << 24);
+    }
+    int f = -1;
+    for (int l = 0; l < 32; l++) if (over[l] && ((pending >> l) & 1u)) { f = l; break; }
+    if (f < 0) {
+      s = (float)apply(incl[31], b.m) * b.u;
+      pending = 0;
+    } else {
+      unsigned m_prev = f == 0 ? b.m : apply(incl[f - 1], b.m);
+      float sf = (float)m_prev * b.u;
+      bool hf = true;
+      float vv[8];
+      for (int k = 0; k < 8; k++) vv[k] = v[f * 8 + k];
+      serial8(vv, vmask[f], sf, hf);
+      s = sf;
+      pending &= ~((2u << f) - 1u);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int gm_debug_fold_f32_host(const float* a, long long n, float* out) {
+  float s = 0.f;
+  bool have = false;
+  for (long long k0 = 0; k0 < n; k0 += 256) {
+    float v[256];
+    unsigned vm[32];
+    for (int l = 0; l < 32; l++) {
+      vm[l] = 0;
+      for (int k = 0; k < 8; k++) {
+        long long i = k0 + l * 8 + k;
+        v[l * 8 + k] = i < n ? a[i] : 0.f;
+        if (i < n) vm[l] |= 1u << k;
+      }
+    }
+    host_warp_fold(v, vm, s, have);
+  }
+  *out = s;
+  return have ? 0 : 2;
+}
+
+__global__ void k_iota(int* p, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+
+// one row holding a[0..n): warps = 1 -> warp-per-row kernel, 16 -> block-per-row kernel; offset shifts the
+// row start inside the index array (exercises the aligned-group masking)
+extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, int offset, float* out) {
+  typedef PageRank<int> P;
+  if (n <= 0 || n >= (1ll << 31) || offset < 0 || offset > 64) { gm_set_error("bad n/offset"); return 1; }
+  float *dx = nullptr, *dy = nullptr;
+  int *dcol = nullptr, *dval = nullptr;
+  long long* dptr = nullptr;
+  unsigned* dbits = nullptr;
+  long long tot = n + offset;
+  cudaMalloc(&dx, tot * 4); cudaMalloc(&dcol, (tot + 16) * 4); cudaMalloc(&dval, (tot + 16) * 4);
+  cudaMalloc(&dptr, 16); cudaMalloc(&dy, 4 * 32); cudaMalloc(&dbits, 4);
+  cudaMemset(dx, 0, tot * 4);
+  cudaMemcpy(dx + offset, a, n * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dval, 0, (tot + 16) * 4);
+  k_iota<<<(unsigned)((tot + 16 + 255) / 256), 256>>>(dcol, tot + 16);
+  long long hp[2] = {offset, tot};
+  cudaMemcpy(dptr, hp, 16, cudaMemcpyHostToDevice);
+  cudaMemset(dbits, 0, 4);
+  cudaMemset(dy, 0, 4 * 32);
+  gm_matrix_view M;
+  memset(&M, 0, sizeof M);
+  M.n_slots = 32; M.n_heavy = 1; M.identity = 1; M.h_ptr = dptr; M.h_col = dcol; M.h_val = dval;
+  P prog;
+  gm::prog_bytes<P> pb = gm::pack(prog);
+  if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, dx, nullptr, dy, dbits);
+  else gm::k_heavy_fadd32<P, float, PR, int, true, true, 16><<<1, 512>>>(pb, M, 0, 1, dx, nullptr, dy, dbits);
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned bits = 0;
+  cudaMemcpy(out, dy, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&bits, dbits, 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy); cudaFree(dcol); cudaFree(dval); cudaFree(dptr); cudaFree(dbits);
+  if (e != cudaSuccess) { gm_set_error(cudaGetErrorString(e)); return 1; }
+  return (bits & 1u) ? 0 : 2;
+}

@@ -332,12 +332,13 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
 
   // heavy prefix / non-empty prefix
   int* cnt = nullptr;
-  if (dalloc(&cnt, 2)) return 1;
-  CK(cudaMemsetAsync(cnt, 0, 8, st));
+  if (dalloc(&cnt, 3)) return 1;
+  CK(cudaMemsetAsync(cnt, 0, 12, st));
   k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, g->heavy_threshold, cnt);
   k_count_nonzero<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, cnt + 1);
-  int hc[2];
-  if (d2h(hc, cnt, 8, st)) return 1;
+  k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, std::max(g->coop_threshold, g->heavy_threshold), cnt + 2);
+  int hc[3];
+  if (d2h(hc, cnt, 12, st)) return 1;
   cudaFree(cnt);
   int n_heavy = std::min(n_pad, (hc[0] + 31) / 32 * 32);
   int n_nonzero = hc[1];
@@ -345,6 +346,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   M.n_slots = n_pad;
   M.n_heavy = n_heavy;
   M.n_slices = n_slices;
+  M.n_coop = std::min(hc[2], n_heavy);
   M.identity = identity ? 1 : 0;
 
   // sort owned edges by (slot, native column)
@@ -364,7 +366,9 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   CK(cudaMemcpyAsync(M.h_ptr, row_ptr, ((size_t)n_heavy + 1) * 8, cudaMemcpyDeviceToDevice, st));
   if (d2h(&nh, row_ptr + n_heavy, 8, st)) return 1;
   E* hv = nullptr;
-  if (dalloc(&M.h_col, nh) || dalloc(&hv, nh)) return 1;
+  if (dalloc(&M.h_col, nh + 16) || dalloc(&hv, nh + 16)) return 1;  // +16: kernels read aligned groups of 8
+  CK(cudaMemsetAsync(M.h_col + nh, 0, 16 * 4, st));
+  CK(cudaMemsetAsync(hv + nh, 0, 16 * sizeof(E), st));
   M.h_val = hv;
   if (nh) k_fill_heavy<E><<<nblk(nh), 256, 0, st>>>(ks, ps, nh, g->d_xidx, val, M.h_col, hv);
 
@@ -404,6 +408,7 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->n_heavy = M.n_heavy;
   v->n_slices = M.n_slices;
   v->identity = M.identity;
+  v->n_coop = M.n_coop;
   v->slot_vertex = M.slot_vertex;
   v->row_len = M.row_len;
   v->h_ptr = M.h_ptr;
@@ -491,6 +496,9 @@ static gm_graph* graph_new(int nvertices, int sizeof_E, int sizeof_V, const gm_g
   g->rank = opts ? opts->rank : 0;
   g->world = (opts && opts->world > 0) ? opts->world : 1;
   g->heavy_threshold = (opts && opts->heavy_threshold > 0) ? opts->heavy_threshold : GM_DEFAULT_HEAVY_THRESHOLD;
+  g->coop_threshold = (opts && opts->coop_threshold > 0) ? opts->coop_threshold : GM_DEFAULT_COOP_THRESHOLD;
+  if (const char* e = getenv("GM_HEAVY_THRESHOLD")) if (!(opts && opts->heavy_threshold > 0)) g->heavy_threshold = atoi(e);
+  if (const char* e = getenv("GM_COOP_THRESHOLD")) if (!(opts && opts->coop_threshold > 0)) g->coop_threshold = atoi(e);
   int per = (nvertices + g->world - 1) / g->world;
   g->n_pad = std::max(32, (per + 31) / 32 * 32);
   g->n_local = nvertices > g->rank ? (nvertices - g->rank + g->world - 1) / g->world : 0;

@@ -9,12 +9,13 @@
 #include "graphmat_b200.h"
 
 #define GM_DEFAULT_HEAVY_THRESHOLD 4096
+#define GM_DEFAULT_COOP_THRESHOLD 16384
 
 void gm_set_error(const std::string& s);
 
 // one operand matrix (device memory owned here); see gm_matrix_view for the meaning
 struct gm_matrix {
-  int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0;
+  int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0, n_coop = 0;
   int* slot_vertex = nullptr;
   int* row_len = nullptr;
   long long* h_ptr = nullptr;
@@ -29,7 +30,7 @@ struct gm_matrix {
 
 struct gm_graph {
   int n = 0, n_local = 0, n_pad = 0, n_full = 0;
-  int rank = 0, world = 1, ref_threads = 4, heavy_threshold = GM_DEFAULT_HEAVY_THRESHOLD;
+  int rank = 0, world = 1, ref_threads = 4, heavy_threshold = GM_DEFAULT_HEAVY_THRESHOLD, coop_threshold = GM_DEFAULT_COOP_THRESHOLD;
   int sizeof_V = 0, sizeof_E = 4;
   long long nnz = 0;
   int first_source = 0;

@@ -28,6 +28,7 @@
 #include <type_traits>
 
 #include "GraphProgram.h"
+#include "gm_fadd32.cuh"
 #include "graphmat_b200.h"
 
 namespace gm {
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(256)
 //   REORDER = true : order-preserving pairwise tree (program declared associative)
 template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool REORDER>
 __global__ void __launch_bounds__(128)
-    k_heavy(prog_bytes<P> pb, gm_matrix_view M, const T* __restrict__ x, const unsigned* __restrict__ xbits,
-            const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+    k_heavy(prog_bytes<P> pb, gm_matrix_view M, int row_begin, const T* __restrict__ x,
+            const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(128)
   const int* __restrict__ cols = M.h_col;
   const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
 
-  for (int slot = warp; slot < M.n_heavy; slot += nwarps) {
+  for (int slot = row_begin + warp; slot < M.n_heavy; slot += nwarps) {
     const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
     if (beg == end) continue;
     const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
@@ -297,6 +298,222 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+
+// ------------------------------ SpMSpV: heavy rows, cooperative (reorderable) --
+// W warps fold one long row.  A lane owns 8 CONSECUTIVE entries (two 128-bit index
+// loads), folds them left to right, the warp combines its 32 partials with an
+// order-preserving tree in shared memory, and thread 0 appends the W warp partials in
+// order to the running value.  Only for programs whose reduce_function is associative.
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int W>
+__global__ void __launch_bounds__(W * 32)
+    k_heavy_coop(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const T* __restrict__ x,
+                 const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
+                 unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  extern __shared__ __align__(16) unsigned char smem[];
+  U* buf = reinterpret_cast<U*>(smem);  // W * 32 partials
+  __shared__ unsigned s_valid[W];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int* __restrict__ cols = M.h_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
+  for (int slot = row_begin + blockIdx.x; slot < row_end; slot += gridDim.x) {
+    const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
+    if (beg == end) continue;
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    V vprop;
+    if (NEEDVP) vprop = vp[vtx];
+    U acc;  // thread 0
+    bool have = false;
+    if (ACCUM && threadIdx.x == 0) {
+      have = test_bit(ybits, vtx);
+      if (have) acc = y[vtx];
+    }
+    for (long long k0 = beg & ~7ll; k0 < end; k0 += W * 256) {
+      const long long i0 = k0 + w * 256 + lane * 8;
+      U part;
+      bool pv = false;
+      if (i0 < end && i0 + 8 > beg) {
+        int c[8];
+        E ev[8];
+        *reinterpret_cast<int4*>(&c[0]) = __ldg(reinterpret_cast<const int4*>(cols + i0));
+        *reinterpret_cast<int4*>(&c[4]) = __ldg(reinterpret_cast<const int4*>(cols + i0 + 4));
+#pragma unroll
+        for (int j = 0; j < 8; j++) ev[j] = vals[i0 + j];
+        T xv[8];
+        bool on[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          on[j] = (i0 + j >= beg) && (i0 + j < end);
+          if (on[j] && !ALLACT) on[j] = test_bit(xbits, c[j]);
+          if (on[j]) xv[j] = x[c[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (on[j]) {
+            if (pv) {
+              U tmp;
+              prog.P::process_message(xv[j], ev[j], vprop, tmp);
+              prog.P::reduce_function(part, tmp);
+            } else {
+              prog.P::process_message(xv[j], ev[j], vprop, part);
+              pv = true;
+            }
+          }
+        }
+      }
+      U* wb = buf + w * 32;
+      if (pv) wb[lane] = part;
+      __syncwarp();
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned vm = __ballot_sync(0xffffffffu, pv);
+        if ((lane & (2 * d - 1)) == 0 && ((vm >> (lane + d)) & 1u)) {
+          if (pv) {
+            U a = wb[lane];
+            prog.P::reduce_function(a, wb[lane + d]);
+            wb[lane] = a;
+          } else {
+            wb[lane] = wb[lane + d];
+            pv = true;
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) s_valid[w] = pv ? 1u : 0u;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int q = 0; q < W; q++) {
+          if (s_valid[q]) {
+            if (have) prog.P::reduce_function(acc, buf[q * 32]);
+            else { acc = buf[q * 32]; have = true; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && have) {
+      y[vtx] = acc;
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    }
+  }
+}
+
+// ------------------------------ SpMSpV: heavy rows, exact fp32 + (gm_fadd32_exact) --
+// Same data movement as k_heavy_coop; the fold is the bit-exact parallel evaluation of
+// the serial fp32 sum (gm_fadd32.cuh).  W = 1: one warp per row, several rows per block.
+template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
+    k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const T* __restrict__ x,
+                   const unsigned* __restrict__ xbits, float* __restrict__ y, unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  constexpr int WPB = (W == 1) ? 4 : W;  // warps per block
+  __shared__ float sm_s;
+  __shared__ int sm_have, sm_ok;
+  __shared__ unsigned sm_d0[WPB], sm_d1[WPB], sm_bad[WPB];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int* __restrict__ cols = M.h_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
+  V vdummy;
+  const int stride = (W == 1) ? gridDim.x * WPB : gridDim.x;
+  for (int slot = row_begin + ((W == 1) ? blockIdx.x * WPB + w : blockIdx.x); slot < row_end; slot += stride) {
+    const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    float s = 0.f;
+    bool have = false;
+    if (W > 1) {
+      if (threadIdx.x == 0) { sm_s = 0.f; sm_have = 0; }
+      __syncthreads();
+    }
+    for (long long k0 = beg & ~7ll; k0 < end; k0 += W * 256) {
+      const long long i0 = k0 + (W == 1 ? 0 : w * 256) + lane * 8;
+      float v[8];
+      unsigned vmask = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = 0.f;
+      if (i0 < end && i0 + 8 > beg) {
+        int c[8];
+        E ev[8];
+        *reinterpret_cast<int4*>(&c[0]) = __ldg(reinterpret_cast<const int4*>(cols + i0));
+        *reinterpret_cast<int4*>(&c[4]) = __ldg(reinterpret_cast<const int4*>(cols + i0 + 4));
+#pragma unroll
+        for (int j = 0; j < 8; j++) ev[j] = vals[i0 + j];
+        T xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          bool on = (i0 + j >= beg) && (i0 + j < end);
+          if (on && !ALLACT) on = test_bit(xbits, c[j]);
+          if (on) { xv[j] = x[c[j]]; vmask |= 1u << j; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if ((vmask >> j) & 1u) prog.P::process_message(xv[j], ev[j], vdummy, v[j]);
+      }
+      if (W == 1) {
+        fx::warp_fold(v, vmask, s, have, lane);
+      } else {
+        s = sm_s;
+        have = sm_have != 0;
+        fx::binade b;
+        bool fast = have && fx::binade_of(s, b);  // block-uniform
+        if (fast) {
+          bool bad = false;
+          fx::qmap mine = fx::identity();
+#pragma unroll
+          for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
+          const fx::qmap incl = fx::warp_scan(mine, lane);
+          const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+          if (lane == 31) { sm_d0[w] = incl.d0; sm_d1[w] = incl.d1; sm_bad[w] = anybad; }
+          __syncthreads();
+          if (w == 0) {
+            fx::qmap t = fx::identity();
+            unsigned bd = 0;
+            if (lane < W) { t.d0 = sm_d0[lane]; t.d1 = sm_d1[lane]; bd = sm_bad[lane]; }
+            t = fx::warp_scan(t, lane);
+            bd = __ballot_sync(0xffffffffu, bd != 0);
+            if (lane == 31) {
+              const unsigned m_end = fx::apply(t, b.m);
+              const int ok = (bd == 0 && m_end < (1u << 24)) ? 1 : 0;
+              sm_ok = ok;
+              if (ok) sm_s = __fmul_rn(__uint2float_rn(m_end), b.u);
+            }
+          }
+          __syncthreads();
+          fast = sm_ok != 0;
+        }
+        if (!fast) {
+          // a warp at a time, each exact for any input (binade crossings, first block of the row, ...)
+#pragma unroll 1
+          for (int q = 0; q < W; q++) {
+            if (w == q) {
+              float sq = sm_s;
+              bool hq = sm_have != 0;
+              fx::warp_fold(v, vmask, sq, hq, lane);
+              if (lane == 0) { sm_s = sq; sm_have = hq ? 1 : 0; }
+            }
+            __syncthreads();
+          }
+        }
+      }
+    }
+    if (W == 1) {
+      if (lane == 0 && have) {
+        y[vtx] = s;
+        atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+      }
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0 && sm_have) {
+        y[vtx] = sm_s;
+        atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ driver --
 #define GM_CUDA_OK(call)                                                                      \
   do {                                                                                        \
@@ -344,6 +561,38 @@ struct engine {
     return 0;
   }
 
+  // heavy rows: [0, n_coop) one thread block per row, [n_coop, n_heavy) one warp per row
+  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+  static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, const T* x, const unsigned* xbits, const V* vp,
+                        U* y, unsigned* ybits, cudaStream_t st, step_counters* sc) {
+    constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
+    constexpr int WC = sizeof(U) <= 16 ? 16 : 4;  // warps per cooperative block (shared memory: WC*32*sizeof(U))
+    const int n_coop = (FADD || REORDER) ? M.n_coop : 0;
+    if (n_coop > 0) {
+      int blocks = n_coop < 148 * 64 ? n_coop : 148 * 64;
+      if constexpr (FADD) {
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, 0, n_coop, x, xbits, (float*)y, ybits);
+      } else {
+        size_t sh = (size_t)WC * 32 * sizeof(U);
+        k_heavy_coop<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, WC><<<blocks, WC * 32, sh, st>>>(pb, M, 0, n_coop, x, xbits, vp, y, ybits);
+      }
+      if (sc) sc->launches++;
+    }
+    if (M.n_heavy > n_coop) {
+      int rows = M.n_heavy - n_coop;
+      int blocks = (rows + 3) / 4;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      if constexpr (FADD) {
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<blocks, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, x, xbits, (float*)y, ybits);
+      } else {
+        size_t sh = 4 * 32 * sizeof(U);
+        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, n_coop, x, xbits, vp, y, ybits);
+      }
+      if (sc) sc->launches++;
+    }
+    return 0;
+  }
+
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
   static int mult_t(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
                     step_counters* sc) {
@@ -353,12 +602,7 @@ struct engine {
     U* y = (U*)vv.y_val;
     prog_bytes<P> pb = pack(prog);
     if (M.n_heavy > 0) {
-      int warps = M.n_heavy;
-      int blocks = (warps + 3) / 4;
-      if (blocks > 148 * 16) blocks = 148 * 16;
-      size_t sh = 4 * 32 * sizeof(U);
-      k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, x, vv.x_bits, vp, y, vv.y_bits);
-      if (sc) sc->launches++;
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, x, vv.x_bits, vp, y, vv.y_bits, st, sc)) return 1;
     }
     if (M.n_slices > 0) {
       int blocks = (M.n_slices + 7) / 8;

@@ -38,7 +38,8 @@ enum { GM_ACTIVE_ONLY = 0, GM_ALL_VERTICES = 1 };
 typedef struct gm_graph_opts {
   int ref_threads;      /* default 4 when 0 */
   int rank, world;      /* tile-row sharding: this process owns 1/world of the rows; default 0,1 */
-  int heavy_threshold;  /* rows longer than this use the row-cooperative kernel; 0 = default */
+  int heavy_threshold;  /* rows longer than this are stored row-contiguous and folded by a warp; 0 = default */
+  int coop_threshold;   /* rows longer than this are folded by a whole thread block; 0 = default */
   int edges_on_device;  /* src/dst/val are device pointers */
   const gm_graph* order_like; /* adopt this graph's vertex placement (needed before gm_graph_share_vertexproperty) */
   int build_mask;       /* bit0: A (IN_EDGES operand), bit1: AT (OUT_EDGES operand); 0 = both (include/Graph.h:226-227) */
@@ -50,6 +51,7 @@ typedef struct gm_graph_opts {
  * NATIVE column id -- the reference's fold order (include/GMDP/singlenode/spmspv.h:55-77). */
 typedef struct gm_matrix_view {
   int n_slots, n_heavy, n_slices, identity;
+  int n_coop;                   /* the first n_coop (longest) heavy rows get one thread block each */
   const int* slot_vertex;       /* slot -> local vertex (unused when identity) */
   const int* row_len;           /* n_slots */
   const long long* h_ptr;       /* n_heavy + 1 */
@@ -170,6 +172,11 @@ enum { GM_REDUCE_REACHABLE = 1,      /* src/BFS.cpp:101-108 etc.: count of verti
        GM_REDUCE_BUCKET_NOT_EMPTY = 2, /* src/DeltaStepping.cpp:109-111, param = bid */
        GM_REDUCE_SQERR = 3 };        /* src/SGD.cpp:158-161: sum of the trailing double (sqerr) */
 int gm_graph_reduce(const gm_graph* g, int what, int param, double* result);
+
+/* ---- test hooks: the bit-exact parallel fp32 fold used for long PageRank rows (gm_fadd32.cuh).
+ * Both return the value of the serial left fold a[0] + a[1] + ... in fp32; status 2 = empty. */
+int gm_debug_fold_f32_host(const float* a, long long n, float* out);
+int gm_debug_fold_f32_device(const float* a, long long n, int warps, int offset, float* out);
 
 #ifdef __cplusplus
 }
