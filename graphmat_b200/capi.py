@@ -54,7 +54,8 @@ class GraphView(C.Structure):
                 ("rank", C.c_int), ("world", C.c_int), ("ref_threads", C.c_int), ("sizeof_V", C.c_int),
                 ("sizeof_E", C.c_int), ("nnz", C.c_longlong), ("vertexproperty", C.c_void_p),
                 ("active_bits", C.c_void_p), ("A", MatrixView), ("AT", MatrixView), ("d_flags", C.c_void_p),
-                ("h_flags", C.c_void_p), ("stream", C.c_void_p)]
+                ("h_flags", C.c_void_p), ("stream", C.c_void_p), ("aux_stream", C.c_void_p), ("ev_fork", C.c_void_p),
+                ("ev_join", C.c_void_p), ("hot_limit", C.c_int)]
 
 
 class VectorsView(C.Structure):

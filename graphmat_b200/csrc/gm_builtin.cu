@@ -251,8 +251,8 @@ extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, 
   M.n_slots = 32; M.n_heavy = 1; M.identity = 1; M.h_ptr = dptr; M.h_col = dcol; M.h_val = dval;
   P prog;
   gm::prog_bytes<P> pb = gm::pack(prog);
-  if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, dx, nullptr, dy, dbits);
-  else gm::k_heavy_fadd32<P, float, PR, int, true, true, 16><<<1, 512>>>(pb, M, 0, 1, dx, nullptr, dy, dbits);
+  if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
+  else gm::k_heavy_fadd32<P, float, PR, int, true, true, 16><<<1, 512>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
   cudaError_t e = cudaDeviceSynchronize();
   unsigned bits = 0;
   cudaMemcpy(out, dy, 4, cudaMemcpyDeviceToHost);

@@ -481,6 +481,11 @@ static int graph_common_alloc(gm_graph* g) {
   CK(cudaMemsetAsync(g->active, 0, (size_t)(g->n_pad >> 5) * 4, st));  // active->setAll(false), Graph.h:236-237
   if (dalloc(&g->d_flags, 16)) return 1;
   CK(cudaMemsetAsync(g->d_flags, 0, 64, st));
+  CK(cudaStreamCreateWithFlags(&g->aux_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+  if (const char* e = getenv("GM_HOT_LIMIT")) g->hot_limit = atoi(e);
+  if (getenv("GM_NO_AUX_STREAM")) { cudaStreamDestroy(g->aux_stream); g->aux_stream = nullptr; }
   CK(cudaMallocHost((void**)&g->h_flags, 64));
   memset(g->h_flags, 0, 64);
   CK(cudaStreamSynchronize(st));
@@ -588,6 +593,9 @@ extern "C" int gm_graph_destroy(gm_graph* g) {
   cudaFree(g->d_flags);
   if (g->h_flags) cudaFreeHost(g->h_flags);
   cudaFree(g->staging);
+  if (g->aux_stream) cudaStreamDestroy(g->aux_stream);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return 0;
@@ -611,6 +619,10 @@ extern "C" int gm_graph_view_get(const gm_graph* g, gm_graph_view* v) {
   v->d_flags = g->d_flags;
   v->h_flags = g->h_flags;
   v->stream = (void*)g->stream;
+  v->aux_stream = (void*)g->aux_stream;
+  v->ev_fork = (void*)g->ev_fork;
+  v->ev_join = (void*)g->ev_join;
+  v->hot_limit = g->hot_limit;
   return 0;
 }
 

@@ -44,7 +44,9 @@ struct gm_graph {
   int* h_flags = nullptr;
   void* staging = nullptr;
   size_t staging_bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int hot_limit = -1;
   gm_allgather_fn allgather = nullptr;
   gm_allreduce_or_fn allreduce_or = nullptr;
   void* xctx = nullptr;

@@ -24,6 +24,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -75,6 +76,61 @@ inline prog_bytes<P> pack(const P& p) {
 
 __device__ __forceinline__ bool test_bit(const unsigned* __restrict__ bits, int i) {
   return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+
+// ---- cache-hinted loads ------------------------------------------------------
+// The index/edge streams are read once per pass: keep them out of L1.  The message
+// vector is stored hot-columns-first, so a gather of x[c] with c < hot_limit is worth
+// an L1 line (evict_last); a cold gather is not (no_allocate) -- otherwise the cold
+// 90 % of the columns, which carry a third of the gathers, thrash the hot set.
+template <class X>
+__device__ __forceinline__ X ld_stream(const X* p) {
+#if defined(GM_STREAM_NO_ALLOCATE)
+  if constexpr (sizeof(X) == 4) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return *reinterpret_cast<X*>(&v);
+  } else if constexpr (sizeof(X) == 8) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return *reinterpret_cast<X*>(&v);
+  } else {
+    return *p;
+  }
+#else
+  if constexpr (sizeof(X) == 4 || sizeof(X) == 8) return __ldg(p);
+  else return *p;
+#endif
+}
+__device__ __forceinline__ int4 ld_stream4(const int* p) {
+#if defined(GM_STREAM_NO_ALLOCATE)
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const int4*>(p));
+#endif
+}
+// hot_limit < 0: plain read-only load (default); >= 0: L1 hint by hotness (experimental)
+template <class X>
+__device__ __forceinline__ X ld_gather(const X* x, int c, int hot_limit) {
+  if constexpr (sizeof(X) == 4) {
+    if (hot_limit < 0) return __ldg(x + c);
+    unsigned v;
+    if (c < hot_limit) asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
+    else asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
+    return *reinterpret_cast<X*>(&v);
+  } else if constexpr (sizeof(X) == 8) {
+    if (hot_limit < 0) return __ldg(x + c);
+    unsigned long long v;
+    if (c < hot_limit) asm volatile("ld.global.nc.L1::evict_last.b64 %0, [%1];" : "=l"(v) : "l"(x + c));
+    else asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(x + c));
+    return *reinterpret_cast<X*>(&v);
+  } else {
+    return x[c];
+  }
 }
 
 // -------------------------------------------------------------------- send --
@@ -136,8 +192,8 @@ __global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
 // UNROLL steps are issued before they are consumed.
 template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
 __global__ void __launch_bounds__(256)
-    k_sell(prog_bytes<P> pb, gm_matrix_view M, const T* __restrict__ x, const unsigned* __restrict__ xbits,
-           const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+    k_sell(prog_bytes<P> pb, gm_matrix_view M, int hot_limit, const T* __restrict__ x,
+           const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -171,15 +227,15 @@ __global__ void __launch_bounds__(256)
       for (int u = 0; u < UNROLL; u++) {
         on[u] = (i + u) < len;
         if (on[u]) {
-          c[u] = __ldg(cp + (long long)(i + u) * 32);
-          ev[u] = ep[(long long)(i + u) * 32];
+          c[u] = ld_stream(cp + (long long)(i + u) * 32);
+          ev[u] = ld_stream(ep + (long long)(i + u) * 32);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
         if (on[u]) {
           if (!ALLACT) on[u] = test_bit(xbits, c[u]);
-          if (on[u]) xv[u] = x[c[u]];
+          if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
         }
       }
 #pragma unroll
@@ -213,7 +269,7 @@ __global__ void __launch_bounds__(256)
 //   REORDER = true : order-preserving pairwise tree (program declared associative)
 template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool REORDER>
 __global__ void __launch_bounds__(128)
-    k_heavy(prog_bytes<P> pb, gm_matrix_view M, int row_begin, const T* __restrict__ x,
+    k_heavy(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int hot_limit, const T* __restrict__ x,
             const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   extern __shared__ __align__(16) unsigned char smem[];
@@ -242,12 +298,12 @@ __global__ void __launch_bounds__(128)
       bool on = idx < end;
       int c = 0;
       if (on) {
-        c = __ldg(cols + idx);
+        c = ld_stream(cols + idx);
         if (!ALLACT) on = test_bit(xbits, c);
       }
       if (on) {
-        T xv = x[c];
-        E ev = vals[idx];
+        T xv = ld_gather(x, c, hot_limit);
+        E ev = ld_stream(vals + idx);
         U tmp;
         prog.P::process_message(xv, ev, vprop, tmp);
         buf[lane] = tmp;
@@ -306,7 +362,7 @@ __global__ void __launch_bounds__(128)
 // order to the running value.  Only for programs whose reduce_function is associative.
 template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int W>
 __global__ void __launch_bounds__(W * 32)
-    k_heavy_coop(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const T* __restrict__ x,
+    k_heavy_coop(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit, const T* __restrict__ x,
                  const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
                  unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
@@ -336,17 +392,17 @@ __global__ void __launch_bounds__(W * 32)
       if (i0 < end && i0 + 8 > beg) {
         int c[8];
         E ev[8];
-        *reinterpret_cast<int4*>(&c[0]) = __ldg(reinterpret_cast<const int4*>(cols + i0));
-        *reinterpret_cast<int4*>(&c[4]) = __ldg(reinterpret_cast<const int4*>(cols + i0 + 4));
+        *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
+        *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
 #pragma unroll
-        for (int j = 0; j < 8; j++) ev[j] = vals[i0 + j];
+        for (int j = 0; j < 8; j++) ev[j] = ld_stream(vals + i0 + j);
         T xv[8];
         bool on[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           on[j] = (i0 + j >= beg) && (i0 + j < end);
           if (on[j] && !ALLACT) on[j] = test_bit(xbits, c[j]);
-          if (on[j]) xv[j] = x[c[j]];
+          if (on[j]) xv[j] = ld_gather(x, c[j], hot_limit);
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -403,14 +459,20 @@ __global__ void __launch_bounds__(W * 32)
 // ------------------------------ SpMSpV: heavy rows, exact fp32 + (gm_fadd32_exact) --
 // Same data movement as k_heavy_coop; the fold is the bit-exact parallel evaluation of
 // the serial fp32 sum (gm_fadd32.cuh).  W = 1: one warp per row, several rows per block.
+// W > 1: the block folds W*256 addends per round.  Every warp scans its 256 under the
+// binade of the block's entry value; warp 0 scans the W warp totals and finds the first
+// warp whose exit value would leave the binade (or that saw an addend the scan cannot
+// prove).  Warps before it are applied, that warp alone runs the warp-level fold from
+// its exact entry value, and the remaining warps are re-scanned under the new binade.
 template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W>
 __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
-    k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const T* __restrict__ x,
-                   const unsigned* __restrict__ xbits, float* __restrict__ y, unsigned* __restrict__ ybits) {
+    k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit,
+                   const T* __restrict__ x, const unsigned* __restrict__ xbits, float* __restrict__ y,
+                   unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   constexpr int WPB = (W == 1) ? 4 : W;  // warps per block
   __shared__ float sm_s;
-  __shared__ int sm_have, sm_ok;
+  __shared__ int sm_have, sm_fail;
   __shared__ unsigned sm_d0[WPB], sm_d1[WPB], sm_bad[WPB];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
@@ -436,16 +498,16 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
       if (i0 < end && i0 + 8 > beg) {
         int c[8];
         E ev[8];
-        *reinterpret_cast<int4*>(&c[0]) = __ldg(reinterpret_cast<const int4*>(cols + i0));
-        *reinterpret_cast<int4*>(&c[4]) = __ldg(reinterpret_cast<const int4*>(cols + i0 + 4));
+        *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
+        *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
 #pragma unroll
-        for (int j = 0; j < 8; j++) ev[j] = vals[i0 + j];
+        for (int j = 0; j < 8; j++) ev[j] = ld_stream(vals + i0 + j);
         T xv[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           bool on = (i0 + j >= beg) && (i0 + j < end);
           if (on && !ALLACT) on = test_bit(xbits, c[j]);
-          if (on) { xv[j] = x[c[j]]; vmask |= 1u << j; }
+          if (on) { xv[j] = ld_gather(x, c[j], hot_limit); vmask |= 1u << j; }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -454,47 +516,67 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
       if (W == 1) {
         fx::warp_fold(v, vmask, s, have, lane);
       } else {
-        s = sm_s;
-        have = sm_have != 0;
-        fx::binade b;
-        bool fast = have && fx::binade_of(s, b);  // block-uniform
-        if (fast) {
-          bool bad = false;
-          fx::qmap mine = fx::identity();
-#pragma unroll
-          for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
-          const fx::qmap incl = fx::warp_scan(mine, lane);
-          const unsigned anybad = __ballot_sync(0xffffffffu, bad);
-          if (lane == 31) { sm_d0[w] = incl.d0; sm_d1[w] = incl.d1; sm_bad[w] = anybad; }
-          __syncthreads();
-          if (w == 0) {
-            fx::qmap t = fx::identity();
-            unsigned bd = 0;
-            if (lane < W) { t.d0 = sm_d0[lane]; t.d1 = sm_d1[lane]; bd = sm_bad[lane]; }
-            t = fx::warp_scan(t, lane);
-            bd = __ballot_sync(0xffffffffu, bd != 0);
-            if (lane == 31) {
-              const unsigned m_end = fx::apply(t, b.m);
-              const int ok = (bd == 0 && m_end < (1u << 24)) ? 1 : 0;
-              sm_ok = ok;
-              if (ok) sm_s = __fmul_rn(__uint2float_rn(m_end), b.u);
-            }
-          }
-          __syncthreads();
-          fast = sm_ok != 0;
-        }
-        if (!fast) {
-          // a warp at a time, each exact for any input (binade crossings, first block of the row, ...)
-#pragma unroll 1
-          for (int q = 0; q < W; q++) {
-            if (w == q) {
-              float sq = sm_s;
-              bool hq = sm_have != 0;
+        // warps of this round that hold at least one addend (block-uniform by construction)
+        const long long wfirst = k0, wspan = end - k0;
+        int nw = (int)((wspan + 255) / 256);
+        if (nw > W) nw = W;
+        (void)wfirst;
+        int first = 0;  // warps [first, nw) are still to be applied
+        while (first < nw) {
+          s = sm_s;
+          have = sm_have != 0;
+          fx::binade b;
+          const bool hot = have && fx::binade_of(s, b);  // block-uniform
+          if (!hot) {
+            // no usable accumulator yet: warp `first` folds its 256 alone (exact for any input)
+            if (w == first) {
+              float sq = s;
+              bool hq = have;
               fx::warp_fold(v, vmask, sq, hq, lane);
               if (lane == 0) { sm_s = sq; sm_have = hq ? 1 : 0; }
             }
+            first++;
             __syncthreads();
+            continue;
           }
+          if (w >= first && w < nw) {
+            bool bad = false;
+            fx::qmap mine = fx::identity();
+#pragma unroll
+            for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
+            const fx::qmap incl = fx::warp_scan(mine, lane);
+            const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+            if (lane == 31) { sm_d0[w] = incl.d0; sm_d1[w] = incl.d1; sm_bad[w] = anybad; }
+          }
+          __syncthreads();
+          if (w == 0) {
+            fx::qmap t = fx::identity();
+            bool bd = false;
+            if (lane >= first && lane < nw) { t.d0 = sm_d0[lane]; t.d1 = sm_d1[lane]; bd = sm_bad[lane] != 0; }
+            t = fx::warp_scan(t, lane);
+            const unsigned m_after = fx::apply(t, b.m);
+            const bool over = (lane >= first && lane < nw) && (bd || m_after >= (1u << 24));
+            const unsigned fail = __ballot_sync(0xffffffffu, over);
+            unsigned m_prev = __shfl_up_sync(0xffffffffu, m_after, 1);
+            if (lane == 0) m_prev = b.m;
+            if (fail == 0) {
+              if (lane == nw - 1) { sm_s = __fmul_rn(__uint2float_rn(m_after), b.u); sm_fail = -1; }
+            } else {
+              const int f = __ffs(fail) - 1;
+              if (lane == f) { sm_s = __fmul_rn(__uint2float_rn(m_prev), b.u); sm_fail = f; }
+            }
+          }
+          __syncthreads();
+          const int f = sm_fail;
+          if (f < 0) break;
+          if (w == f) {
+            float sq = sm_s;
+            bool hq = true;
+            fx::warp_fold(v, vmask, sq, hq, lane);
+            if (lane == 0) sm_s = sq;
+          }
+          first = f + 1;
+          __syncthreads();
         }
       }
     }
@@ -563,30 +645,31 @@ struct engine {
 
   // heavy rows: [0, n_coop) one thread block per row, [n_coop, n_heavy) one warp per row
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
-  static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, const T* x, const unsigned* xbits, const V* vp,
-                        U* y, unsigned* ybits, cudaStream_t st, step_counters* sc) {
+  static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, int hot, const T* x, const unsigned* xbits,
+                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc) {
     constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
     constexpr int WC = sizeof(U) <= 16 ? 16 : 4;  // warps per cooperative block (shared memory: WC*32*sizeof(U))
     const int n_coop = (FADD || REORDER) ? M.n_coop : 0;
-    if (n_coop > 0) {
+    static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
+    if (n_coop > 0 && !(dbg & 1)) {
       int blocks = n_coop < 148 * 64 ? n_coop : 148 * 64;
       if constexpr (FADD) {
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, 0, n_coop, x, xbits, (float*)y, ybits);
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, 0, n_coop, hot, x, xbits, (float*)y, ybits);
       } else {
         size_t sh = (size_t)WC * 32 * sizeof(U);
-        k_heavy_coop<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, WC><<<blocks, WC * 32, sh, st>>>(pb, M, 0, n_coop, x, xbits, vp, y, ybits);
+        k_heavy_coop<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, WC><<<blocks, WC * 32, sh, st>>>(pb, M, 0, n_coop, hot, x, xbits, vp, y, ybits);
       }
       if (sc) sc->launches++;
     }
-    if (M.n_heavy > n_coop) {
+    if (M.n_heavy > n_coop && !(dbg & 2)) {
       int rows = M.n_heavy - n_coop;
       int blocks = (rows + 3) / 4;
       if (blocks > 148 * 16) blocks = 148 * 16;
       if constexpr (FADD) {
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<blocks, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, x, xbits, (float*)y, ybits);
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<blocks, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits);
       } else {
         size_t sh = 4 * 32 * sizeof(U);
-        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, n_coop, x, xbits, vp, y, ybits);
+        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, n_coop, hot, x, xbits, vp, y, ybits);
       }
       if (sc) sc->launches++;
     }
@@ -601,14 +684,27 @@ struct engine {
     const V* vp = (const V*)gv.vertexproperty;
     U* y = (U*)vv.y_val;
     prog_bytes<P> pb = pack(prog);
-    if (M.n_heavy > 0) {
-      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, x, vv.x_bits, vp, y, vv.y_bits, st, sc)) return 1;
+    const int hot = gv.hot_limit;
+    // heavy rows and sliced-ELL rows are disjoint: run them concurrently on two streams
+    cudaStream_t sh = gv.aux_stream ? (cudaStream_t)gv.aux_stream : st;
+    const bool fork = M.n_heavy > 0 && M.n_slices > 0 && sh != st;
+    if (fork) {
+      GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_fork, st));
+      GM_CUDA_OK(cudaStreamWaitEvent(sh, (cudaEvent_t)gv.ev_fork, 0));
     }
-    if (M.n_slices > 0) {
+    if (M.n_heavy > 0) {
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc)) return 1;
+    }
+    static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
+    if (M.n_slices > 0 && !(dbg & 4)) {
       int blocks = (M.n_slices + 7) / 8;
       if (blocks > 148 * 8) blocks = 148 * 8;
-      k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, M, x, vv.x_bits, vp, y, vv.y_bits);
+      k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits);
       if (sc) sc->launches++;
+    }
+    if (fork) {
+      GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_join, sh));
+      GM_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)gv.ev_join, 0));
     }
     if (sc) sc->edges += M.nnz;
     GM_CUDA_OK(cudaGetLastError());

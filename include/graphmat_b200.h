@@ -73,6 +73,9 @@ typedef struct gm_graph_view {
   int* d_flags;                 /* device scratch: [0] = "some vertex changed" */
   int* h_flags;                 /* pinned host mirror */
   void* stream;                 /* cudaStream_t all work is ordered on */
+  void* aux_stream;             /* second stream: heavy rows run beside the sliced-ELL rows */
+  void* ev_fork; void* ev_join; /* cudaEvent_t pair ordering the two streams */
+  int hot_limit;                /* x indices below this are gathered with an L1-resident hint */
 } gm_graph_view;
 
 typedef struct gm_vectors_view {
