@@ -218,6 +218,17 @@ __global__ void __launch_bounds__(256)
     }
     const int* cp = cols + base + lane;
     const E* ep = vals + base + lane;
+    // two-stage software pipeline: the index/edge loads of batch i+1 are in flight while
+    // the gathers of batch i are, so a lane's chain never waits for two round trips
+    int cn[UNROLL];
+    E evn[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      if (u < len) {
+        cn[u] = ld_stream(cp + (long long)u * 32);
+        evn[u] = ld_stream(ep + (long long)u * 32);
+      }
+    }
     for (int i = 0; i < width; i += UNROLL) {
       int c[UNROLL];
       E ev[UNROLL];
@@ -225,17 +236,19 @@ __global__ void __launch_bounds__(256)
       T xv[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
+        c[u] = cn[u];
+        ev[u] = evn[u];
         on[u] = (i + u) < len;
         if (on[u]) {
-          c[u] = ld_stream(cp + (long long)(i + u) * 32);
-          ev[u] = ld_stream(ep + (long long)(i + u) * 32);
+          if (!ALLACT) on[u] = test_bit(xbits, c[u]);
+          if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
-        if (on[u]) {
-          if (!ALLACT) on[u] = test_bit(xbits, c[u]);
-          if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
+        if (i + UNROLL + u < len) {
+          cn[u] = ld_stream(cp + (long long)(i + UNROLL + u) * 32);
+          evn[u] = ld_stream(ep + (long long)(i + UNROLL + u) * 32);
         }
       }
 #pragma unroll
