@@ -44,7 +44,7 @@ class RunStats(C.Structure):
 
 class MatrixView(C.Structure):
     _fields_ = [("n_slots", C.c_int), ("n_heavy", C.c_int), ("n_slices", C.c_int), ("identity", C.c_int),
-                ("n_coop", C.c_int), ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
+                ("n_coop", C.c_int), ("n_slices_wide", C.c_int), ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
                 ("nnz", C.c_longlong)]
 

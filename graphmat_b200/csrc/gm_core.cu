@@ -332,13 +332,14 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
 
   // heavy prefix / non-empty prefix
   int* cnt = nullptr;
-  if (dalloc(&cnt, 3)) return 1;
-  CK(cudaMemsetAsync(cnt, 0, 12, st));
+  if (dalloc(&cnt, 4)) return 1;
+  CK(cudaMemsetAsync(cnt, 0, 16, st));
+  k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, 31, cnt + 3);  // rows with >= 32 entries
   k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, g->heavy_threshold, cnt);
   k_count_nonzero<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, cnt + 1);
   k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, std::max(g->coop_threshold, g->heavy_threshold), cnt + 2);
-  int hc[3];
-  if (d2h(hc, cnt, 12, st)) return 1;
+  int hc[4];
+  if (d2h(hc, cnt, 16, st)) return 1;
   cudaFree(cnt);
   int n_heavy = std::min(n_pad, (hc[0] + 31) / 32 * 32);
   int n_nonzero = hc[1];
@@ -347,6 +348,7 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   M.n_heavy = n_heavy;
   M.n_slices = n_slices;
   M.n_coop = std::min(hc[2], n_heavy);
+  M.n_slices_wide = hc[3] > n_heavy ? std::min(n_slices, (hc[3] - n_heavy + 31) / 32) : 0;
   M.identity = identity ? 1 : 0;
 
   // sort owned edges by (slot, native column)
@@ -409,6 +411,7 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->n_slices = M.n_slices;
   v->identity = M.identity;
   v->n_coop = M.n_coop;
+  v->n_slices_wide = M.n_slices_wide;
   v->slot_vertex = M.slot_vertex;
   v->row_len = M.row_len;
   v->h_ptr = M.h_ptr;

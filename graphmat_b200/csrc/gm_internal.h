@@ -15,7 +15,7 @@ void gm_set_error(const std::string& s);
 
 // one operand matrix (device memory owned here); see gm_matrix_view for the meaning
 struct gm_matrix {
-  int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0, n_coop = 0;
+  int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0, n_coop = 0, n_slices_wide = 0;
   int* slot_vertex = nullptr;
   int* row_len = nullptr;
   long long* h_ptr = nullptr;

@@ -119,13 +119,13 @@ __device__ __forceinline__ X ld_gather(const X* x, int c, int hot_limit) {
   if constexpr (sizeof(X) == 4) {
     if (hot_limit < 0) return __ldg(x + c);
     unsigned v;
-    if (c < hot_limit) asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
+    if (c < hot_limit) return __ldg(x + c);
     else asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
     return *reinterpret_cast<X*>(&v);
   } else if constexpr (sizeof(X) == 8) {
     if (hot_limit < 0) return __ldg(x + c);
     unsigned long long v;
-    if (c < hot_limit) asm volatile("ld.global.nc.L1::evict_last.b64 %0, [%1];" : "=l"(v) : "l"(x + c));
+    if (c < hot_limit) return __ldg(x + c);
     else asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(x + c));
     return *reinterpret_cast<X*>(&v);
   } else {
@@ -190,19 +190,22 @@ __global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
 // ------------------------------------------------------- SpMSpV: sliced ELL --
 // One row per lane.  The fold is a private left-to-right chain per lane; loads of
 // UNROLL steps are issued before they are consumed.
-template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+// Launch shape: block b, warp w folds slices [slice_begin + (8b + w) * spw, + spw).  Slices are
+// stored longest first and blocks are dispatched in order, so the hardware block scheduler gives
+// longest-processing-time-first load balance for free; spw > 1 only for the short-row tail.
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int UNROLL>
 __global__ void __launch_bounds__(256)
-    k_sell(prog_bytes<P> pb, gm_matrix_view M, int hot_limit, const T* __restrict__ x,
-           const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+    k_sell(prog_bytes<P> pb, gm_matrix_view M, int slice_begin, int slice_end, int spw, int hot_limit,
+           const T* __restrict__ x, const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
+           unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int* __restrict__ cols = M.s_col;
   const E* __restrict__ vals = reinterpret_cast<const E*>(M.s_val);
-  constexpr int UNROLL = (sizeof(T) <= 8) ? 8 : 1;
-
-  for (int s = warp; s < M.n_slices; s += nwarps) {
+  int s = slice_begin + warp * spw;
+  const int s_end = min(s + spw, slice_end);
+  for (; s < s_end; s++) {
     const int slot = M.n_heavy + s * 32 + lane;
     const int len = __ldg(M.row_len + slot);
     const long long base = __ldg(M.slice_ptr + s);
@@ -218,17 +221,6 @@ __global__ void __launch_bounds__(256)
     }
     const int* cp = cols + base + lane;
     const E* ep = vals + base + lane;
-    // two-stage software pipeline: the index/edge loads of batch i+1 are in flight while
-    // the gathers of batch i are, so a lane's chain never waits for two round trips
-    int cn[UNROLL];
-    E evn[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      if (u < len) {
-        cn[u] = ld_stream(cp + (long long)u * 32);
-        evn[u] = ld_stream(ep + (long long)u * 32);
-      }
-    }
     for (int i = 0; i < width; i += UNROLL) {
       int c[UNROLL];
       E ev[UNROLL];
@@ -236,19 +228,17 @@ __global__ void __launch_bounds__(256)
       T xv[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
-        c[u] = cn[u];
-        ev[u] = evn[u];
         on[u] = (i + u) < len;
         if (on[u]) {
-          if (!ALLACT) on[u] = test_bit(xbits, c[u]);
-          if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
+          c[u] = ld_stream(cp + (long long)(i + u) * 32);
+          ev[u] = ld_stream(ep + (long long)(i + u) * 32);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
-        if (i + UNROLL + u < len) {
-          cn[u] = ld_stream(cp + (long long)(i + UNROLL + u) * 32);
-          evn[u] = ld_stream(ep + (long long)(i + UNROLL + u) * 32);
+        if (on[u]) {
+          if (!ALLACT) on[u] = test_bit(xbits, c[u]);
+          if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
         }
       }
 #pragma unroll
@@ -620,6 +610,20 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     }                                                                                         \
   } while (0)
 
+#ifndef GM_DEFAULT_HOT_CACHE
+#define GM_DEFAULT_HOT_CACHE 0
+#endif
+inline int gm_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 struct step_counters {
   long long launches = 0;
   long long edges = 0;
@@ -676,8 +680,7 @@ struct engine {
     }
     if (M.n_heavy > n_coop && !(dbg & 2)) {
       int rows = M.n_heavy - n_coop;
-      int blocks = (rows + 3) / 4;
-      if (blocks > 148 * 16) blocks = 148 * 16;
+      int blocks = (rows + 3) / 4;  // one row per warp, blocks dispatched longest rows first
       if constexpr (FADD) {
         k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<blocks, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits);
       } else {
@@ -710,10 +713,23 @@ struct engine {
     }
     static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
     if (M.n_slices > 0 && !(dbg & 4)) {
-      int blocks = (M.n_slices + 7) / 8;
-      if (blocks > 148 * 8) blocks = 148 * 8;
-      k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits);
-      if (sc) sc->launches++;
+      // wide slices: one per warp, deep unroll (a lane's chain waits for loads once per UNROLL
+      // steps); narrow tail: several slices per warp so blocks stay worth their launch
+      constexpr int UW = (sizeof(T) <= 8 && sizeof(U) <= 8) ? 16 : 1;
+      constexpr int UN = (sizeof(T) <= 8 && sizeof(U) <= 8) ? 8 : 1;
+      static const int spw_tail = getenv("GM_SELL_SPW") ? atoi(getenv("GM_SELL_SPW")) : 8;
+      const int nw = M.n_slices_wide < M.n_slices ? M.n_slices_wide : M.n_slices;
+      if (nw > 0) {
+        k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW><<<(nw + 7) / 8, 256, 0, st>>>(
+            pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        if (sc) sc->launches++;
+      }
+      if (M.n_slices > nw) {
+        const int warps = (M.n_slices - nw + spw_tail - 1) / spw_tail;
+        k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN><<<(warps + 7) / 8, 256, 0, st>>>(
+            pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        if (sc) sc->launches++;
+      }
     }
     if (fork) {
       GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_join, sh));

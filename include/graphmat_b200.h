@@ -52,6 +52,7 @@ typedef struct gm_graph_opts {
 typedef struct gm_matrix_view {
   int n_slots, n_heavy, n_slices, identity;
   int n_coop;                   /* the first n_coop (longest) heavy rows get one thread block each */
+  int n_slices_wide;            /* leading slices whose rows hold >= 32 entries (one warp each) */
   const int* slot_vertex;       /* slot -> local vertex (unused when identity) */
   const int* row_len;           /* n_slots */
   const long long* h_ptr;       /* n_heavy + 1 */
