@@ -152,10 +152,15 @@ __global__ void __launch_bounds__(256) k_send(prog_bytes<P> pb, int n_pad, const
 }
 
 // ------------------------------------------------------------------- apply --
-template <class P, class U, class V>
-__global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_pad, const U* __restrict__ y,
+// FUSE (ALL_VERTICES programs that do not override do_every_iteration): every vertex is active
+// again in the next iteration, so the same pass also produces the next message vector
+// (send_message on the fresh property) and re-arms the active set: one sweep over the vertex
+// properties per iteration instead of three kernels.
+template <class P, class T, class U, class V, bool FUSE>
+__global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, int n_pad, const U* __restrict__ y,
                                                const unsigned* __restrict__ ybits, V* __restrict__ vp,
-                                               unsigned* __restrict__ active, int* __restrict__ flags) {
+                                               unsigned* __restrict__ active, int* __restrict__ flags,
+                                               T* __restrict__ x, unsigned* __restrict__ xbits) {
   alignas(16) unsigned char pbuf[sizeof(P)];
   memcpy(pbuf, pb.b, sizeof(P));
   P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
@@ -169,10 +174,26 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_pad, cons
     prog.P::apply(y[i], cur);
     changed = (old != cur);
     vp[i] = cur;
+    if (FUSE) {
+      T t;
+      (void)prog.P::send_message(cur, t);
+      x[i] = t;
+    }
+  } else if (FUSE && i < n_valid) {
+    T t;
+    (void)prog.P::send_message(vp[i], t);
+    x[i] = t;
   }
   unsigned m = __ballot_sync(0xffffffffu, changed);
   if ((i & 31) == 0) {
-    active[i >> 5] = m;  // setAllInactive + set where changed
+    if (FUSE) {
+      const int lo = i;
+      unsigned all = lo + 32 <= n_valid ? 0xffffffffu : (lo < n_valid ? (1u << (n_valid - lo)) - 1u : 0u);
+      active[i >> 5] = all;  // setAllActive of the next iteration (GraphMatRuntime.h:250-252)
+      xbits[i >> 5] = all;
+    } else {
+      active[i >> 5] = m;  // setAllInactive + set where changed
+    }
     if (m && *((volatile int*)flags) == 0) atomicExch(flags, 1);
   }
 }
@@ -776,12 +797,23 @@ struct engine {
     exit(1);
   }
 
+  // true when P inherits GraphProgram's empty do_every_iteration: program state cannot change
+  // between apply and the next send, so the two may share a kernel
+  static constexpr bool NO_HOOK =
+      std::is_same<decltype(&P::do_every_iteration), void (GraphMat::GraphProgram<T, U, V, E>::*)(int)>::value;
+
   // the apply loop   GraphMatRuntime.h:184-226 (flag = !converged)
-  static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc) {
+  static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc, bool fuse_send = false) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     const int n = gv.n_local_pad;
-    k_apply<P, U, V><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), n, (const U*)vv.y_val, vv.y_bits, (V*)gv.vertexproperty,
-                                                     gv.active_bits, gv.d_flags);
+    T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
+    unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
+    if (fuse_send)
+      k_apply<P, T, U, V, true><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
+                                                                (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
+    else
+      k_apply<P, T, U, V, false><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
+                                                                 (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
     if (sc) sc->launches++;
     GM_CUDA_OK(cudaGetLastError());
     return 0;
@@ -817,18 +849,19 @@ struct engine {
     GM_CUDA_OK(cudaEventCreate(&s1));
     float ms_spmv = 0.f;
     const bool all = prog.getActivity() == GraphMat::ALL_VERTICES;
+    const bool fuse = all && NO_HOOK && !getenv("GM_NO_FUSE");
     GM_CUDA_OK(cudaEventRecord(e0, st));
     if (all && set_all_active(gv, &sc)) return 1;
     int it = 0, converged = 1;
     while (1) {
       GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
-      if (send(prog, gv, vv, &sc)) return 1;
+      if (!(fuse && it > 0) && send(prog, gv, vv, &sc)) return 1;  // fused: the previous apply already sent
       if (gv.world > 1 && gm_graph_exchange_x(g, tmp)) return 1;
       const bool timing = stats != nullptr;
       if (timing) GM_CUDA_OK(cudaEventRecord(s0, st));
       if (spmspv(prog, gv, vv, all, &sc)) return 1;
       if (timing) GM_CUDA_OK(cudaEventRecord(s1, st));
-      if (apply(prog, gv, vv, &sc)) return 1;
+      if (apply(prog, gv, vv, &sc, fuse)) return 1;
       GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
       GM_CUDA_OK(cudaStreamSynchronize(st));
       int changed = gv.h_flags[0];
@@ -840,7 +873,7 @@ struct engine {
         ms_spmv += t;
       }
       prog.do_every_iteration(it);
-      if (all && set_all_active(gv, &sc)) return 1;
+      if (all && !fuse && set_all_active(gv, &sc)) return 1;
       it++;
       if (it == iterations) break;
       if (iterations <= 0 && converged) break;
