@@ -46,7 +46,8 @@ class MatrixView(C.Structure):
     _fields_ = [("n_slots", C.c_int), ("n_heavy", C.c_int), ("n_slices", C.c_int), ("identity", C.c_int),
                 ("n_coop", C.c_int), ("n_slices_wide", C.c_int), ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
-                ("nnz", C.c_longlong)]
+                ("nnz", C.c_longlong), ("n_segs", C.c_int), ("seg_len", C.c_int), ("seg_ptr", C.c_void_p),
+                ("seg_row", C.c_void_p)]
 
 
 class GraphView(C.Structure):
@@ -89,7 +90,7 @@ SYMBOLS = [
     "gm_graph_set_all_inactive", "gm_graph_set_active", "gm_graph_set_inactive", "gm_graph_set_all_vertexproperty",
     "gm_graph_set_vertexproperty", "gm_graph_get_vertexproperty", "gm_graph_set_vertexproperties",
     "gm_graph_get_vertexproperties", "gm_graph_share_vertexproperty", "gm_graph_vertex_owner",
-    "gm_graph_out_degree_source", "gm_vectors_create", "gm_vectors_destroy", "gm_vectors_view_get",
+    "gm_graph_out_degree_source", "gm_vectors_create", "gm_vectors_destroy", "gm_vectors_view_get", "gm_vectors_scratch",
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
     "gm_debug_fold_f32_device",

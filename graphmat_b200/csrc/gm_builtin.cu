@@ -95,7 +95,7 @@ int dispatch(const call& c) {
     if (EN::send(prog, gv, vv, nullptr)) return 1;
     if (gv.world > 1 && gm_graph_exchange_x(c.g, c.tmp)) return 1;
   } else if (c.op == OP_SPMSPV) {
-    if (EN::spmspv(prog, gv, vv, false, nullptr)) return 1;
+    if (EN::spmspv(prog, gv, vv, false, nullptr, c.tmp)) return 1;
   } else {
     if (cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st) != cudaSuccess) return 1;
     if (EN::apply(prog, gv, vv, nullptr)) return 1;

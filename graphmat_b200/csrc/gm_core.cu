@@ -136,6 +136,16 @@ __global__ void k_slice_width(const int* row_len, int n_heavy, int n_slices, lon
   if (s < n_slices) out[s] = 32ll * row_len[n_heavy + s * 32];
 }
 
+__global__ void k_seg_count(const long long* h_ptr, int n_heavy, int seg_len, int* cnt) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_heavy) cnt[r] = (int)((h_ptr[r + 1] - h_ptr[r] + seg_len - 1) / seg_len);
+}
+__global__ void k_seg_rows(const int* seg_ptr, int n_heavy, int* seg_row) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_heavy) return;
+  for (int k = seg_ptr[r]; k < seg_ptr[r + 1]; k++) seg_row[k] = r;
+}
+
 template <class E>
 __global__ void k_fill_heavy(const unsigned long long* keys, const unsigned* payload, long long cnt, const int* xidx,
                              const E* val, int* h_col, E* h_val) {
@@ -290,6 +300,8 @@ static void matrix_free(gm_matrix& M) {
   cudaFree(M.slice_ptr);
   cudaFree(M.s_col);
   cudaFree(M.s_val);
+  cudaFree(M.seg_ptr);
+  cudaFree(M.seg_row);
   M = gm_matrix();
 }
 
@@ -374,6 +386,28 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   M.h_val = hv;
   if (nh) k_fill_heavy<E><<<nblk(nh), 256, 0, st>>>(ks, ps, nh, g->d_xidx, val, M.h_col, hv);
 
+  // segments of the heavy rows (two-phase fold for associative programs)
+  M.seg_len = GM_SEG_LEN;
+  M.n_segs = 0;
+  if (dalloc(&M.seg_ptr, (size_t)n_heavy + 1)) return 1;
+  CK(cudaMemsetAsync(M.seg_ptr, 0, ((size_t)n_heavy + 1) * 4, st));
+  if (n_heavy > 0) {
+    int* segcnt = nullptr;
+    if (dalloc(&segcnt, (size_t)n_heavy + 1)) return 1;
+    CK(cudaMemsetAsync(segcnt, 0, ((size_t)n_heavy + 1) * 4, st));
+    k_seg_count<<<nblk(n_heavy), 256, 0, st>>>(M.h_ptr, n_heavy, M.seg_len, segcnt);
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, segcnt, M.seg_ptr, n_heavy + 1, st));
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, tb ? tb : 1));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tb, segcnt, M.seg_ptr, n_heavy + 1, st));
+    if (d2h(&M.n_segs, M.seg_ptr + n_heavy, 4, st)) return 1;
+    cudaFree(tmp);
+    cudaFree(segcnt);
+  }
+  if (dalloc(&M.seg_row, (size_t)M.n_segs)) return 1;
+  if (M.n_segs) k_seg_rows<<<nblk(n_heavy), 256, 0, st>>>(M.seg_ptr, n_heavy, M.seg_row);
+
   // sliced ELL for the rest
   long long* widths = nullptr;
   if (dalloc(&widths, (size_t)n_slices + 1) || dalloc(&M.slice_ptr, (size_t)n_slices + 1)) return 1;
@@ -421,6 +455,10 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->s_col = M.s_col;
   v->s_val = M.s_val;
   v->nnz = M.nnz;
+  v->n_segs = M.n_segs;
+  v->seg_len = M.seg_len;
+  v->seg_ptr = M.seg_ptr;
+  v->seg_row = M.seg_row;
 }
 
 // d_src/d_dst: device copies owned by this call (public ids, overwritten with native ids)
@@ -430,6 +468,14 @@ static int build_graph(gm_graph* g, int* d_src, int* d_dst, const E* d_val, long
   cudaStream_t st = g->stream;
   const int n = g->n;
   const int npart = g->ref_threads * 16;
+  if (g->heavy_auto) {
+    // A sliced-ELL lane folds its row as one serial chain (~1.5 us per 16 entries): keep the longest
+    // chain well under the time the whole pass needs (~nnz / 3e11 s), i.e. threshold ~ nnz * 1e-5.
+    long long per_rank = nnz / g->world;
+    int t = 256;
+    while (t < GM_DEFAULT_HEAVY_THRESHOLD && (long long)t * 2 <= per_rank / 100000) t *= 2;
+    g->heavy_threshold = t;
+  }
   // first public vertex with an out-edge (the benchmark's BFS/SSSP source)
   g->first_source = 0;
   if (nnz) {
@@ -505,7 +551,8 @@ static gm_graph* graph_new(int nvertices, int sizeof_E, int sizeof_V, const gm_g
   g->world = (opts && opts->world > 0) ? opts->world : 1;
   g->heavy_threshold = (opts && opts->heavy_threshold > 0) ? opts->heavy_threshold : GM_DEFAULT_HEAVY_THRESHOLD;
   g->coop_threshold = (opts && opts->coop_threshold > 0) ? opts->coop_threshold : GM_DEFAULT_COOP_THRESHOLD;
-  if (const char* e = getenv("GM_HEAVY_THRESHOLD")) if (!(opts && opts->heavy_threshold > 0)) g->heavy_threshold = atoi(e);
+  g->heavy_auto = !(opts && opts->heavy_threshold > 0);
+  if (const char* e = getenv("GM_HEAVY_THRESHOLD")) if (g->heavy_auto) { g->heavy_threshold = atoi(e); g->heavy_auto = false; }
   if (const char* e = getenv("GM_COOP_THRESHOLD")) if (!(opts && opts->coop_threshold > 0)) g->coop_threshold = atoi(e);
   int per = (nvertices + g->world - 1) / g->world;
   g->n_pad = std::max(32, (per + 31) / 32 * 32);
@@ -833,6 +880,7 @@ extern "C" int gm_vectors_destroy(gm_vectors* v) {
   cudaFree(v->x_bits);
   cudaFree(v->y_val);
   cudaFree(v->y_bits);
+  cudaFree(v->scratch);
   delete v;
   return 0;
 }
@@ -843,6 +891,18 @@ extern "C" int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* o) {
   o->x_bits = v->x_bits;
   o->y_val = v->y_val;
   o->y_bits = v->y_bits;
+  return 0;
+}
+
+extern "C" int gm_vectors_scratch(gm_vectors* v, long long bytes, void** out) {
+  if ((size_t)bytes > v->scratch_bytes) {
+    cudaFree(v->scratch);
+    v->scratch = nullptr;
+    v->scratch_bytes = 0;
+    CK(cudaMalloc(&v->scratch, (size_t)bytes));
+    v->scratch_bytes = (size_t)bytes;
+  }
+  *out = v->scratch;
   return 0;
 }
 

@@ -10,6 +10,7 @@
 
 #define GM_DEFAULT_HEAVY_THRESHOLD 4096
 #define GM_DEFAULT_COOP_THRESHOLD 16384
+#define GM_SEG_LEN 2048
 
 void gm_set_error(const std::string& s);
 
@@ -26,6 +27,9 @@ struct gm_matrix {
   void* s_val = nullptr;
   long long nnz = 0;
   long long s_entries = 0;  // padded sliced-ELL entries
+  int n_segs = 0, seg_len = 0;
+  int* seg_ptr = nullptr;
+  int* seg_row = nullptr;
 };
 
 struct gm_graph {
@@ -34,6 +38,7 @@ struct gm_graph {
   int sizeof_V = 0, sizeof_E = 4;
   long long nnz = 0;
   int first_source = 0;
+  bool heavy_auto = true;
   int* d_xidx = nullptr;    // native id -> x index (owner * n_pad + local)
   std::vector<int> h_xidx;  // lazily mirrored for single-vertex accessors
   void* vp = nullptr;
@@ -58,5 +63,7 @@ struct gm_vectors {
   unsigned* x_bits = nullptr;
   void* y_val = nullptr;
   unsigned* y_bits = nullptr;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
 };
 #endif

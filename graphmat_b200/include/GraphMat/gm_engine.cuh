@@ -480,6 +480,141 @@ __global__ void __launch_bounds__(W * 32)
   }
 }
 
+
+// ------------------- SpMSpV: heavy rows in two phases (associative programs) --
+// Phase 1, k_heavy_seg: heavy rows are cut into segments of seg_len consecutive entries; a warp
+// folds one segment (lane L the L-th run of seg_len/32 consecutive entries, left to right; then an
+// order-preserving tree over the 32 lane partials) into partial[seg].  Phase 2, k_heavy_combine:
+// a warp folds the partials of one row, again as ordered lane runs + ordered tree, and appends the
+// result to y.  Order is preserved everywhere, only the association changes, so this is exact for
+// min / integer + / "last writer" and within rounding for fp64 sums.  Any row length is spread over
+// as many warps as it has segments: no tail behind the longest row.
+template <class U, class P>
+__device__ __forceinline__ void warp_ordered_tree(const P& prog, U* wb, U& part, bool& pv, int lane) {
+  if (pv) wb[lane] = part;
+  __syncwarp();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned vm = __ballot_sync(0xffffffffu, pv);
+    if ((lane & (2 * d - 1)) == 0 && ((vm >> (lane + d)) & 1u)) {
+      if (pv) {
+        U a = wb[lane];
+        prog.P::reduce_function(a, wb[lane + d]);
+        wb[lane] = a;
+      } else {
+        wb[lane] = wb[lane + d];
+        pv = true;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT>
+__global__ void __launch_bounds__(128)
+    k_heavy_seg(prog_bytes<P> pb, gm_matrix_view M, int hot_limit, const T* __restrict__ x,
+                const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ partial,
+                unsigned char* __restrict__ pvalid) {
+  const P& prog = pb.get();
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  U* wb = reinterpret_cast<U*>(smem) + wib * 32;
+  const int seg = blockIdx.x * 4 + wib;
+  if (seg >= M.n_segs) return;
+  const int row = __ldg(M.seg_row + seg);
+  const long long rbeg = __ldg(M.h_ptr + row), rend = __ldg(M.h_ptr + row + 1);
+  const long long sbeg = rbeg + (long long)(seg - __ldg(M.seg_ptr + row)) * M.seg_len;
+  const long long send = min(sbeg + M.seg_len, rend);
+  const int run = M.seg_len >> 5;
+  long long i = sbeg + (long long)lane * run;
+  const long long iend = min(i + run, send);
+  const int* __restrict__ cols = M.h_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
+  V vprop;
+  if (NEEDVP) vprop = vp[IDENT ? row : __ldg(M.slot_vertex + row)];
+  U part;
+  bool pv = false;
+  constexpr int UNROLL = sizeof(T) <= 8 ? 8 : 1;
+  for (; i < iend; i += UNROLL) {
+    int c[UNROLL];
+    E ev[UNROLL];
+    bool on[UNROLL];
+    T xv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      on[u] = i + u < iend;
+      if (on[u]) {
+        c[u] = ld_stream(cols + i + u);
+        ev[u] = ld_stream(vals + i + u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      if (on[u]) {
+        if (!ALLACT) on[u] = test_bit(xbits, c[u]);
+        if (on[u]) xv[u] = ld_gather(x, c[u], hot_limit);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      if (on[u]) {
+        if (pv) {
+          U tmp;
+          prog.P::process_message(xv[u], ev[u], vprop, tmp);
+          prog.P::reduce_function(part, tmp);
+        } else {
+          prog.P::process_message(xv[u], ev[u], vprop, part);
+          pv = true;
+        }
+      }
+    }
+  }
+  warp_ordered_tree<U, P>(prog, wb, part, pv, lane);
+  if (lane == 0) {
+    pvalid[seg] = pv ? 1 : 0;
+    if (pv) partial[seg] = wb[0];
+  }
+}
+
+template <class P, class U, bool IDENT, bool ACCUM>
+__global__ void __launch_bounds__(128)
+    k_heavy_combine(prog_bytes<P> pb, gm_matrix_view M, const U* __restrict__ partial,
+                    const unsigned char* __restrict__ pvalid, U* __restrict__ y, unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  U* wb = reinterpret_cast<U*>(smem) + wib * 32;
+  const int row = blockIdx.x * 4 + wib;
+  if (row >= M.n_heavy) return;
+  const int s0 = __ldg(M.seg_ptr + row), s1 = __ldg(M.seg_ptr + row + 1);
+  if (s0 == s1) return;
+  const int vtx = IDENT ? row : __ldg(M.slot_vertex + row);
+  const int run = (s1 - s0 + 31) >> 5;
+  int k = s0 + lane * run;
+  const int kend = min(k + run, s1);
+  U part;
+  bool pv = false;
+  for (; k < kend; k++) {
+    if (pvalid[k]) {
+      if (pv) prog.P::reduce_function(part, partial[k]);
+      else { part = partial[k]; pv = true; }
+    }
+  }
+  warp_ordered_tree<U, P>(prog, wb, part, pv, lane);
+  if (lane == 0 && pv) {
+    if (ACCUM && test_bit(ybits, vtx)) {
+      U a = y[vtx];
+      prog.P::reduce_function(a, wb[0]);
+      y[vtx] = a;
+    } else {
+      y[vtx] = wb[0];
+    }
+    atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+  }
+}
+
 // ------------------------------ SpMSpV: heavy rows, exact fp32 + (gm_fadd32_exact) --
 // Same data movement as k_heavy_coop; the fold is the bit-exact parallel evaluation of
 // the serial fp32 sum (gm_fadd32.cuh).  W = 1: one warp per row, several rows per block.
@@ -681,41 +816,51 @@ struct engine {
     return 0;
   }
 
-  // heavy rows: [0, n_coop) one thread block per row, [n_coop, n_heavy) one warp per row
+  // heavy rows.  fp32-sum programs: exact parallel fold, [0, n_coop) one thread block per row,
+  // [n_coop, n_heavy) one warp per row.  Associative programs: two-phase segmented fold.
+  // Anything else: one warp per row, batches folded serially (exact for any reduce_function).
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
   static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, int hot, const T* x, const unsigned* xbits,
-                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc) {
+                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc, gm_vectors* vecs) {
     constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
-    constexpr int WC = sizeof(U) <= 16 ? 16 : 4;  // warps per cooperative block (shared memory: WC*32*sizeof(U))
-    const int n_coop = (FADD || REORDER) ? M.n_coop : 0;
     static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
-    if (n_coop > 0 && !(dbg & 1)) {
-      int blocks = n_coop < 148 * 64 ? n_coop : 148 * 64;
-      if constexpr (FADD) {
+    if constexpr (FADD) {
+      const int n_coop = M.n_coop;
+      if (n_coop > 0 && !(dbg & 1)) {
+        int blocks = n_coop < 148 * 64 ? n_coop : 148 * 64;
         k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, 0, n_coop, hot, x, xbits, (float*)y, ybits);
-      } else {
-        size_t sh = (size_t)WC * 32 * sizeof(U);
-        k_heavy_coop<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, WC><<<blocks, WC * 32, sh, st>>>(pb, M, 0, n_coop, hot, x, xbits, vp, y, ybits);
+        if (sc) sc->launches++;
       }
-      if (sc) sc->launches++;
-    }
-    if (M.n_heavy > n_coop && !(dbg & 2)) {
-      int rows = M.n_heavy - n_coop;
-      int blocks = (rows + 3) / 4;  // one row per warp, blocks dispatched longest rows first
-      if constexpr (FADD) {
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<blocks, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits);
-      } else {
+      if (M.n_heavy > n_coop && !(dbg & 2)) {
+        int rows = M.n_heavy - n_coop;
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<(rows + 3) / 4, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits);
+        if (sc) sc->launches++;
+      }
+    } else if constexpr (REORDER) {
+      if (M.n_segs > 0 && !(dbg & 1)) {
+        void* scratch = nullptr;
+        const size_t pbytes = ((size_t)M.n_segs * sizeof(U) + 255) & ~(size_t)255;
+        if (gm_vectors_scratch(vecs, (long long)(pbytes + M.n_segs), &scratch)) return 1;
+        U* partial = (U*)scratch;
+        unsigned char* pvalid = (unsigned char*)scratch + pbytes;
+        const size_t sh = 4 * 32 * sizeof(U);
+        k_heavy_seg<P, T, U, V, E, ALLACT, NEEDVP, IDENT><<<(M.n_segs + 3) / 4, 128, sh, st>>>(pb, M, hot, x, xbits, vp, partial, pvalid);
+        k_heavy_combine<P, U, IDENT, ACCUM><<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, partial, pvalid, y, ybits);
+        if (sc) sc->launches += 2;
+      }
+    } else {
+      if (!(dbg & 1)) {
         size_t sh = 4 * 32 * sizeof(U);
-        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, REORDER><<<blocks, 128, sh, st>>>(pb, M, n_coop, hot, x, xbits, vp, y, ybits);
+        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, false><<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, 0, hot, x, xbits, vp, y, ybits);
+        if (sc) sc->launches++;
       }
-      if (sc) sc->launches++;
     }
     return 0;
   }
 
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
   static int mult_t(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
-                    step_counters* sc) {
+                    step_counters* sc, gm_vectors* vecs) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     const T* x = (const T*)vv.x_val;
     const V* vp = (const V*)gv.vertexproperty;
@@ -730,7 +875,7 @@ struct engine {
       GM_CUDA_OK(cudaStreamWaitEvent(sh, (cudaEvent_t)gv.ev_fork, 0));
     }
     if (M.n_heavy > 0) {
-      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc)) return 1;
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc, vecs)) return 1;
     }
     static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
     if (M.n_slices > 0 && !(dbg & 4)) {
@@ -763,10 +908,10 @@ struct engine {
 
   // mult_segment / mult_segment3 for one operand matrix   SPMV.h:62-95
   static int mult(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
-                  bool allact, bool accum, step_counters* sc) {
+                  bool allact, bool accum, step_counters* sc, gm_vectors* vecs) {
     const bool needvp = prog.getProcessMessageRequiresVertexprop();
     const bool ident = M.identity != 0;
-#define GM_MULT(A_, N_, I_, C_) return mult_t<A_, N_, I_, C_>(prog, gv, M, vv, sc)
+#define GM_MULT(A_, N_, I_, C_) return mult_t<A_, N_, I_, C_>(prog, gv, M, vv, sc, vecs)
 #define GM_MULT_C(A_, N_, I_) \
   do { if (accum) GM_MULT(A_, N_, I_, true); else GM_MULT(A_, N_, I_, false); } while (0)
 #define GM_MULT_I(A_, N_) \
@@ -783,15 +928,16 @@ struct engine {
   }
 
   // SpMTSpV / SpMSpV selection   GraphMatRuntime.h:160-176
-  static int spmspv(const P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, bool allact, step_counters* sc) {
+  static int spmspv(const P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, bool allact, step_counters* sc,
+                    gm_vectors* vecs) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
     const int order = (int)prog.getOrder();
-    if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc);
-    if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc);
+    if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc, vecs);
+    if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc, vecs);
     if (order == GraphMat::ALL_EDGES) {
-      if (mult(prog, gv, gv.AT, vv, allact, false, sc)) return 1;
-      return mult(prog, gv, gv.A, vv, allact, true, sc);
+      if (mult(prog, gv, gv.AT, vv, allact, false, sc, vecs)) return 1;
+      return mult(prog, gv, gv.A, vv, allact, true, sc, vecs);
     }
     printf("Unrecognized option \n");
     exit(1);
@@ -859,7 +1005,7 @@ struct engine {
       if (gv.world > 1 && gm_graph_exchange_x(g, tmp)) return 1;
       const bool timing = stats != nullptr;
       if (timing) GM_CUDA_OK(cudaEventRecord(s0, st));
-      if (spmspv(prog, gv, vv, all, &sc)) return 1;
+      if (spmspv(prog, gv, vv, all, &sc, tmp)) return 1;
       if (timing) GM_CUDA_OK(cudaEventRecord(s1, st));
       if (apply(prog, gv, vv, &sc, fuse)) return 1;
       GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));

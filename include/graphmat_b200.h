@@ -62,6 +62,9 @@ typedef struct gm_matrix_view {
   const int* s_col;
   const void* s_val;
   long long nnz;                /* entries owned by this rank */
+  int n_segs, seg_len;          /* heavy rows cut into segments of seg_len entries (associative programs) */
+  const int* seg_ptr;           /* n_heavy + 1: first segment of each heavy row */
+  const int* seg_row;           /* n_segs: heavy row of each segment */
 } gm_matrix_view;
 
 typedef struct gm_graph_view {
@@ -133,6 +136,7 @@ int gm_graph_out_degree_source(const gm_graph* g, int* v);            /* first p
 int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int sizeof_U);
 int gm_vectors_destroy(gm_vectors* v);
 int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* out);
+int gm_vectors_scratch(gm_vectors* v, long long bytes, void** out);   /* device scratch, grown on demand */
 
 /* ---- multi-GPU exchange (replaces the MPI sends of include/GMDP/multinode/spmspv.h:61-116 and the
  *      Allreduce of include/GraphMatRuntime.h:226).  The library calls these between send and SpMSpV /
