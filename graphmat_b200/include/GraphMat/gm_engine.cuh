@@ -117,7 +117,11 @@ __device__ __forceinline__ int4 ld_stream4(const int* p) {
 template <class X>
 __device__ __forceinline__ X ld_gather(const X* x, int c, int hot_limit) {
   if constexpr (sizeof(X) == 4) {
-    if (hot_limit < 0) return __ldg(x + c);
+    if (hot_limit == -1) return __ldg(x + c);
+    if (hot_limit < -1) {  // experiment only (GM_HOT_LIMIT=-K): what a perfect on-SM cache of K columns would buy
+      if (c < -hot_limit) return __ldg(x + (c & 63));  // always an L1 hit
+      return __ldg(x + c);
+    }
     unsigned v;
     if (c < hot_limit) return __ldg(x + c);
     else asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
@@ -755,6 +759,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
   }
 }
 
+}  // namespace gm
+#include "gm_pass.cuh"
+namespace gm {
+
 // ------------------------------------------------------------------ driver --
 #define GM_CUDA_OK(call)                                                                      \
   do {                                                                                        \
@@ -766,8 +774,8 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     }                                                                                         \
   } while (0)
 
-#ifndef GM_DEFAULT_HOT_CACHE
-#define GM_DEFAULT_HOT_CACHE 0
+#ifndef GM_DEFAULT_PASS_HOT
+#define GM_DEFAULT_PASS_HOT 0
 #endif
 inline int gm_sm_count() {
   static int n = 0;
@@ -867,6 +875,30 @@ struct engine {
     U* y = (U*)vv.y_val;
     prog_bytes<P> pb = pack(prog);
     const int hot = gv.hot_limit;
+    // fp32-sum programs: the whole pass as one persistent kernel with a shared-memory copy of the
+    // hottest columns of x (gm_pass.cuh); GM_PASS_HOT = bytes of shared memory per SM, 0 = separate kernels
+    if constexpr (is_fadd32<P>::value && std::is_same<T, float>::value && std::is_same<U, float>::value && !NEEDVP &&
+                  !ACCUM) {
+      static const int pass_bytes = getenv("GM_PASS_HOT") ? atoi(getenv("GM_PASS_HOT")) : GM_DEFAULT_PASS_HOT;
+      static const int pass_min = getenv("GM_PASS_MIN_SLICES") ? atoi(getenv("GM_PASS_MIN_SLICES")) : 148 * 64;
+      if (pass_bytes > 0 && M.n_slices >= pass_min) {
+        int hot_n = pass_bytes / (int)sizeof(T);
+        if (hot_n > gv.n_full) hot_n = gv.n_full;
+        hot_n &= ~3;
+        auto kern = k_pass_fadd32<P, T, V, E, ALLACT, IDENT>;
+        static bool attr_set = false;
+        if (!attr_set) {
+          GM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr_set = true;
+        }
+        int* counters = gv.d_flags + 4;
+        GM_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
+        kern<<<gm_sm_count(), 1024, (size_t)hot_n * sizeof(T), st>>>(pb, M, hot_n, 32, counters, x, vv.x_bits, (float*)y, vv.y_bits);
+        if (sc) { sc->launches++; sc->edges += M.nnz; }
+        GM_CUDA_OK(cudaGetLastError());
+        return 0;
+      }
+    }
     // heavy rows and sliced-ELL rows are disjoint: run them concurrently on two streams
     cudaStream_t sh = gv.aux_stream ? (cudaStream_t)gv.aux_stream : st;
     const bool fork = M.n_heavy > 0 && M.n_slices > 0 && sh != st;
