@@ -39,7 +39,8 @@ class GraphOpts(C.Structure):
 
 class RunStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("ms_total", C.c_float), ("ms_spmv", C.c_float),
-                ("kernel_launches", C.c_longlong), ("edges_processed", C.c_longlong)]
+                ("kernel_launches", C.c_longlong), ("edges_processed", C.c_longlong),
+                ("push_passes", C.c_longlong)]
 
 
 class MatrixView(C.Structure):
@@ -47,7 +48,8 @@ class MatrixView(C.Structure):
                 ("n_coop", C.c_int), ("n_slices_wide", C.c_int), ("slot_vertex", C.c_void_p), ("row_len", C.c_void_p), ("h_ptr", C.c_void_p), ("h_col", C.c_void_p),
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
                 ("nnz", C.c_longlong), ("n_segs", C.c_int), ("seg_len", C.c_int), ("seg_ptr", C.c_void_p),
-                ("seg_row", C.c_void_p)]
+                ("seg_row", C.c_void_p), ("c_ptr", C.c_void_p), ("c_row", C.c_void_p), ("c_rank", C.c_void_p),
+                ("c_val", C.c_void_p), ("rank_bits", C.c_int)]
 
 
 class GraphView(C.Structure):
@@ -56,7 +58,8 @@ class GraphView(C.Structure):
                 ("sizeof_E", C.c_int), ("nnz", C.c_longlong), ("vertexproperty", C.c_void_p),
                 ("active_bits", C.c_void_p), ("A", MatrixView), ("AT", MatrixView), ("d_flags", C.c_void_p),
                 ("h_flags", C.c_void_p), ("stream", C.c_void_p), ("aux_stream", C.c_void_p), ("ev_fork", C.c_void_p),
-                ("ev_join", C.c_void_p), ("hot_limit", C.c_int)]
+                ("ev_join", C.c_void_p), ("hot_limit", C.c_int), ("owner", C.c_void_p),
+                ("push_divisor", C.c_int), ("push_min_nnz", C.c_longlong)]
 
 
 class VectorsView(C.Structure):
@@ -93,7 +96,8 @@ SYMBOLS = [
     "gm_graph_out_degree_source", "gm_vectors_create", "gm_vectors_destroy", "gm_vectors_view_get", "gm_vectors_scratch",
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
-    "gm_debug_fold_f32_device",
+    "gm_debug_fold_f32_device", "gm_graph_push_ready", "gm_graph_set_push_policy", "gm_push_count", "gm_push_prepare",
+    "gm_push_sort",
 ]
 
 
@@ -252,6 +256,14 @@ class Graph:
     def share_vertexproperty(self, owner):
         _check(lib().gm_graph_share_vertexproperty(self.h, owner.h), "gm_graph_share_vertexproperty")
         self._keep.append(owner)
+
+    def push_ready(self, which=1):
+        """Build the column-major companion used for sparse frontiers (0 = A, 1 = AT) ahead of the first run."""
+        _check(lib().gm_graph_push_ready(self.h, C.c_int(which)), "gm_graph_push_ready")
+
+    def set_push_policy(self, divisor=16, min_nnz=1 << 18):
+        """Sparse-frontier path when frontier entries * divisor <= nnz and nnz >= min_nnz; divisor 0 = never."""
+        _check(lib().gm_graph_set_push_policy(self.h, C.c_int(divisor), C.c_longlong(min_nnz)), "gm_graph_set_push_policy")
 
     def first_source(self):
         v = C.c_int()

@@ -292,6 +292,10 @@ static int exclusive_scan_ll(const long long* in, long long* out, int n, cudaStr
 
 // ------------------------------------------------------------- matrix build --
 static void matrix_free(gm_matrix& M) {
+  cudaFree(M.c_ptr);
+  cudaFree(M.c_row);
+  cudaFree(M.c_rank);
+  cudaFree(M.c_val);
   cudaFree(M.slot_vertex);
   cudaFree(M.row_len);
   cudaFree(M.h_ptr);
@@ -459,6 +463,11 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->seg_len = M.seg_len;
   v->seg_ptr = M.seg_ptr;
   v->seg_row = M.seg_row;
+  v->c_ptr = M.c_ptr;
+  v->c_row = M.c_row;
+  v->c_rank = M.c_rank;
+  v->c_val = M.c_val;
+  v->rank_bits = M.rank_bits;
 }
 
 // d_src/d_dst: device copies owned by this call (public ids, overwritten with native ids)
@@ -534,6 +543,8 @@ static int graph_common_alloc(gm_graph* g) {
   CK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   if (const char* e = getenv("GM_HOT_LIMIT")) g->hot_limit = atoi(e);
+  if (const char* e = getenv("GM_PUSH_DIVISOR")) g->push_divisor = atoi(e);
+  if (const char* e = getenv("GM_PUSH_MIN_NNZ")) g->push_min_nnz = atoll(e);
   if (getenv("GM_NO_AUX_STREAM")) { cudaStreamDestroy(g->aux_stream); g->aux_stream = nullptr; }
   CK(cudaMallocHost((void**)&g->h_flags, 64));
   memset(g->h_flags, 0, 64);
@@ -638,6 +649,7 @@ extern "C" int gm_graph_destroy(gm_graph* g) {
   matrix_free(g->A);
   matrix_free(g->AT);
   cudaFree(g->d_xidx);
+  cudaFree(g->push_scratch);
   if (g->vp_owner) cudaFree(g->vp);
   cudaFree(g->active);
   cudaFree(g->d_flags);
@@ -673,6 +685,9 @@ extern "C" int gm_graph_view_get(const gm_graph* g, gm_graph_view* v) {
   v->ev_fork = (void*)g->ev_fork;
   v->ev_join = (void*)g->ev_join;
   v->hot_limit = g->hot_limit;
+  v->owner = const_cast<gm_graph*>(g);
+  v->push_divisor = g->push_divisor;
+  v->push_min_nnz = g->push_min_nnz;
   return 0;
 }
 
@@ -852,6 +867,247 @@ extern "C" int gm_graph_share_vertexproperty(gm_graph* g, gm_graph* owner) {
   if (g->vp_owner) cudaFree(g->vp);
   g->vp = owner->vp;
   g->vp_owner = false;
+  return 0;
+}
+
+
+// ------------------------------------------------- sparse frontiers (push) --
+// Column-major companion of one operand matrix, derived on the device from the row-major arrays:
+// every entry becomes (x index; row slot, position in the row's fold order, edge value), sorted by
+// x index.  The position ("rank") lets the push path fold a row's contributions in exactly the
+// order the row-major kernels (and the reference, spmspv.h:55-77) use.
+__global__ void k_csc_emit_heavy(const long long* h_ptr, const int* h_col, const unsigned* h_val, int n_heavy,
+                                 unsigned* key, unsigned* eidx, int* row, int* rank, unsigned* val) {
+  int r = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;  // warp per row
+  if (r >= n_heavy) return;
+  long long b = h_ptr[r], e = h_ptr[r + 1];
+  for (long long i = b + lane; i < e; i += 32) {
+    key[i] = (unsigned)h_col[i];
+    eidx[i] = (unsigned)i;
+    row[i] = r;
+    rank[i] = (int)(i - b);
+    val[i] = h_val[i];
+  }
+}
+__global__ void k_csc_emit_sell(const long long* slice_ptr, const int* s_col, const unsigned* s_val, const int* row_len,
+                                const long long* row_off, int n_heavy, int n_rows, long long nh, unsigned* key,
+                                unsigned* eidx, int* row, int* rank, unsigned* val) {
+  int rel = blockIdx.x * blockDim.x + threadIdx.x;  // thread per sliced-ELL row: a warp reads one slice step coalesced
+  if (rel >= n_rows) return;
+  int slot = n_heavy + rel;
+  int len = row_len[slot];
+  long long base = slice_ptr[rel >> 5] + (rel & 31);
+  long long out = nh + row_off[rel];
+  for (int i = 0; i < len; i++) {
+    long long pos = base + 32ll * i;
+    key[out + i] = (unsigned)s_col[pos];
+    eidx[out + i] = (unsigned)(out + i);
+    row[out + i] = slot;
+    rank[out + i] = i;
+    val[out + i] = s_val[pos];
+  }
+}
+__global__ void k_csc_fill(const unsigned* key, const unsigned* eidx, const int* row, const int* rank, const unsigned* val,
+                           long long total, int* c_row, int* c_rank, unsigned* c_val, long long* c_cnt) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  unsigned e = eidx[i];
+  c_row[i] = row[e];
+  c_rank[i] = rank[e];
+  c_val[i] = val[e];
+  atomicAdd((unsigned long long*)(c_cnt + key[i]), 1ull);
+}
+__global__ void k_len_slice_to_ll(const int* row_len, int first, int n, long long* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = row_len[first + i];
+}
+
+static int build_push(gm_graph* g, gm_matrix& M) {
+  if (M.push_built) return 0;
+  cudaStream_t st = g->stream;
+  if (g->sizeof_E != 4) {
+    gm_set_error("push companion: only 4-byte edge values are supported");
+    return 1;
+  }
+  const long long total = M.nnz;
+  if (total >= (1ll << 32)) {
+    gm_set_error("push companion: more than 2^32 entries per rank");
+    return 1;
+  }
+  const int n_rows = M.n_slices > 0 ? std::min(M.n_slices * 32, M.n_slots - M.n_heavy) : 0;
+  long long nh = 0;
+  if (M.n_heavy > 0 && d2h(&nh, M.h_ptr + M.n_heavy, 8, st)) return 1;
+  int maxlen = 0;
+  if (M.n_slots > 0 && d2h(&maxlen, M.row_len, 4, st)) return 1;  // rows are stored longest first
+  M.rank_bits = std::max(1, ceil_log2((long long)maxlen + 1));
+  unsigned *k0 = nullptr, *k1 = nullptr, *e0 = nullptr, *e1 = nullptr, *val = nullptr, *ks = nullptr, *es = nullptr;
+  int *row = nullptr, *rank = nullptr;
+  long long *len_ll = nullptr, *row_off = nullptr, *cnt = nullptr;
+  if (dalloc(&k0, total) || dalloc(&k1, total) || dalloc(&e0, total) || dalloc(&e1, total) || dalloc(&val, total) ||
+      dalloc(&row, total) || dalloc(&rank, total))
+    return 1;
+  if (nh > 0)
+    k_csc_emit_heavy<<<nblk((long long)M.n_heavy * 32), 256, 0, st>>>(M.h_ptr, M.h_col, (const unsigned*)M.h_val, M.n_heavy,
+                                                                     k0, e0, row, rank, val);
+  if (n_rows > 0) {
+    if (dalloc(&len_ll, (size_t)n_rows + 1) || dalloc(&row_off, (size_t)n_rows + 1)) return 1;
+    CK(cudaMemsetAsync(len_ll, 0, ((size_t)n_rows + 1) * 8, st));
+    k_len_slice_to_ll<<<nblk(n_rows), 256, 0, st>>>(M.row_len, M.n_heavy, n_rows, len_ll);
+    if (exclusive_scan_ll(len_ll, row_off, n_rows, st)) return 1;
+    k_csc_emit_sell<<<nblk(n_rows), 256, 0, st>>>(M.slice_ptr, M.s_col, (const unsigned*)M.s_val, M.row_len, row_off,
+                                                 M.n_heavy, n_rows, nh, k0, e0, row, rank, val);
+  }
+  CK(cudaGetLastError());
+  if (total > 0 && sort_pairs(k0, k1, e0, e1, total, std::max(1, ceil_log2(g->n_full)), st, &ks, &es)) return 1;
+  unsigned* cv = nullptr;
+  if (dalloc(&M.c_row, total) || dalloc(&M.c_rank, total) || dalloc(&cv, total) || dalloc(&cnt, (size_t)g->n_full + 1) ||
+      dalloc(&M.c_ptr, (size_t)g->n_full + 1))
+    return 1;
+  M.c_val = cv;
+  CK(cudaMemsetAsync(cnt, 0, ((size_t)g->n_full + 1) * 8, st));
+  if (total > 0) k_csc_fill<<<nblk(total), 256, 0, st>>>(ks, es, row, rank, val, total, M.c_row, M.c_rank, cv, cnt);
+  CK(cudaGetLastError());
+  if (exclusive_scan_ll(cnt, M.c_ptr, g->n_full, st)) return 1;
+  cudaFree(k0); cudaFree(k1); cudaFree(e0); cudaFree(e1); cudaFree(val); cudaFree(row); cudaFree(rank);
+  cudaFree(len_ll); cudaFree(row_off); cudaFree(cnt);
+  M.push_built = true;
+  return 0;
+}
+
+static gm_matrix* which_matrix(gm_graph* g, int which) { return which == 0 ? &g->A : &g->AT; }
+
+extern "C" int gm_graph_set_push_policy(gm_graph* g, int divisor, long long min_nnz) {
+  g->push_divisor = divisor < 0 ? 0 : divisor;
+  g->push_min_nnz = min_nnz < 0 ? 0 : min_nnz;
+  return 0;
+}
+extern "C" int gm_graph_push_ready(gm_graph* g, int which) {
+  gm_matrix* M = which_matrix(g, which);
+  if (M->n_slots == 0) {
+    gm_set_error("push companion: this operand matrix was not built (build_mask)");
+    return 1;
+  }
+  return build_push(g, *M);
+}
+
+// frontier statistics: active columns that own entries here, and how many entries they have
+__global__ void k_push_count(const unsigned* __restrict__ xbits, int n_words, const long long* __restrict__ c_ptr,
+                             unsigned long long* out) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long cols = 0, ents = 0;
+  if (w < n_words) {
+    unsigned m = xbits[w];
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      long long d = c_ptr[w * 32 + b + 1] - c_ptr[w * 32 + b];
+      if (d > 0) { cols++; ents += (unsigned long long)d; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    cols += __shfl_down_sync(0xffffffffu, cols, o);
+    ents += __shfl_down_sync(0xffffffffu, ents, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cols) {
+    atomicAdd(out, cols);
+    atomicAdd(out + 1, ents);
+  }
+}
+__global__ void k_push_compact(const unsigned* __restrict__ xbits, int n_words, const long long* __restrict__ c_ptr,
+                               int* counter, int* f_col, long long* f_deg) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned m = xbits[w];
+  while (m) {
+    int b = __ffs(m) - 1;
+    m &= m - 1;
+    long long d = c_ptr[w * 32 + b + 1] - c_ptr[w * 32 + b];
+    if (d > 0) {
+      int p = atomicAdd(counter, 1);
+      f_col[p] = w * 32 + b;
+      f_deg[p] = d;
+    }
+  }
+}
+
+extern "C" int gm_push_count(gm_graph* g, int which, const gm_vectors* v, int* n_active, long long* n_entries) {
+  gm_matrix* M = which_matrix(g, which);
+  if (build_push(g, *M)) return 1;
+  cudaStream_t st = g->stream;
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(g->d_flags + 8);
+  CK(cudaMemsetAsync(d, 0, 16, st));
+  const int n_words = g->n_full >> 5;
+  k_push_count<<<nblk(n_words), 256, 0, st>>>(v->x_bits, n_words, M->c_ptr, d);
+  CK(cudaGetLastError());
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(g->h_flags + 8);  // pinned: no staging copy
+  if (d2h(h, d, 16, st)) return 1;
+  *n_active = (int)h[0];
+  *n_entries = (long long)h[1];
+  return 0;
+}
+
+extern "C" int gm_push_prepare(gm_graph* g, int which, gm_vectors* v, int n_active, long long n_entries,
+                               gm_push_plan* plan) {
+  gm_matrix* M = which_matrix(g, which);
+  if (!M->push_built) {
+    gm_set_error("gm_push_prepare before gm_push_count");
+    return 1;
+  }
+  cudaStream_t st = g->stream;
+  memset(plan, 0, sizeof *plan);
+  plan->n_active = n_active;
+  plan->n_entries = n_entries;
+  int slot_bits = std::max(1, ceil_log2(M->n_slots));
+  plan->key_bits = std::min(64, slot_bits + M->rank_bits);
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t scan_tb = 0, sort_tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_tb, (long long*)nullptr, (long long*)nullptr, n_active + 1, st));
+  {
+    cub::DoubleBuffer<unsigned long long> kb(nullptr, nullptr);
+    cub::DoubleBuffer<unsigned> vb(nullptr, nullptr);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_tb, kb, vb, n_entries, 0, plan->key_bits, st));
+  }
+  const size_t tmp_b = up(std::max(scan_tb, sort_tb));
+  const size_t b_col = up((size_t)n_active * 4), b_off = up(((size_t)n_active + 1) * 8);
+  const size_t b_key = up((size_t)n_entries * 8), b_ord = up((size_t)n_entries * 4), b_val = up((size_t)n_entries * v->sizeof_U);
+  const size_t need = b_col + b_off + 2 * b_key + 2 * b_ord + b_val + tmp_b;
+  if (need > g->push_scratch_bytes) {  // kept in the graph: run_graph_program may create its vectors per call
+    CK(cudaStreamSynchronize(st));
+    cudaFree(g->push_scratch);
+    g->push_scratch = nullptr;
+    g->push_scratch_bytes = 0;
+    const size_t want = std::max(need + need / 2, (size_t)1 << 22);
+    CK(cudaMalloc(&g->push_scratch, want));
+    g->push_scratch_bytes = want;
+  }
+  unsigned char* p = (unsigned char*)g->push_scratch;
+  plan->f_col = (int*)p; p += b_col;
+  plan->f_off = (long long*)p; p += b_off;
+  plan->keys = (unsigned long long*)p; p += b_key;
+  plan->keys_alt = (unsigned long long*)p; p += b_key;
+  plan->order = (unsigned*)p; p += b_ord;
+  plan->order_alt = (unsigned*)p; p += b_ord;
+  plan->vals = p; p += b_val;
+  plan->sort_tmp = p;
+  plan->sort_tmp_bytes = (long long)tmp_b;
+  int* counter = g->d_flags + 12;
+  CK(cudaMemsetAsync(counter, 0, 4, st));
+  CK(cudaMemsetAsync(plan->f_off + n_active, 0, 8, st));
+  const int n_words = g->n_full >> 5;
+  k_push_compact<<<nblk(n_words), 256, 0, st>>>(v->x_bits, n_words, M->c_ptr, counter, plan->f_col, plan->f_off);
+  CK(cudaGetLastError());
+  size_t tb = tmp_b;
+  CK(cub::DeviceScan::ExclusiveSum(plan->sort_tmp, tb, plan->f_off, plan->f_off, n_active + 1, st));
+  return 0;
+}
+
+extern "C" int gm_push_sort(gm_graph* g, gm_push_plan* plan) {
+  cub::DoubleBuffer<unsigned long long> kb(plan->keys, plan->keys_alt);
+  cub::DoubleBuffer<unsigned> vb(plan->order, plan->order_alt);
+  size_t tb = (size_t)plan->sort_tmp_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(plan->sort_tmp, tb, kb, vb, plan->n_entries, 0, plan->key_bits, g->stream));
+  if (kb.Current() != plan->keys) std::swap(plan->keys, plan->keys_alt);
+  if (vb.Current() != plan->order) std::swap(plan->order, plan->order_alt);
   return 0;
 }
 

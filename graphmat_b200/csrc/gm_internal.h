@@ -30,6 +30,13 @@ struct gm_matrix {
   int n_segs = 0, seg_len = 0;
   int* seg_ptr = nullptr;
   int* seg_row = nullptr;
+  // column-major companion for sparse frontiers (built on first use, gm_graph_push_ready)
+  long long* c_ptr = nullptr;  // n_full + 1
+  int* c_row = nullptr;        // row slot of each entry
+  int* c_rank = nullptr;       // position of the entry in its row's fold order
+  void* c_val = nullptr;       // edge value
+  int rank_bits = 0;           // bits needed for c_rank
+  bool push_built = false;
 };
 
 struct gm_graph {
@@ -52,6 +59,10 @@ struct gm_graph {
   cudaStream_t stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int hot_limit = -1;
+  void* push_scratch = nullptr;  // triples + sort buffers of the sparse-frontier path, grown geometrically
+  size_t push_scratch_bytes = 0;
+  int push_divisor = 16;
+  long long push_min_nnz = 1ll << 18;
   gm_allgather_fn allgather = nullptr;
   gm_allreduce_or_fn allreduce_or = nullptr;
   void* xctx = nullptr;

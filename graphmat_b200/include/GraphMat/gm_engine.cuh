@@ -27,6 +27,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <vector>
+#include <algorithm>
 
 #include "GraphProgram.h"
 #include "gm_fadd32.cuh"
@@ -52,6 +54,14 @@ template <class P, class = void>
 struct is_reorderable : std::false_type {};
 template <class P>
 struct is_reorderable<P, typename std::enable_if<P::gm_reorderable>::type> : std::true_type {};
+// `static const bool gm_last_writer = true;`: reduce_function(a, b) is `a = b` (BFS, src/BFS.cpp:72-74).
+// The left fold in ascending column order then keeps the contribution of the LAST active entry of
+// the row, and process_message is const (GraphProgram.h:79), so a sparse-x pass may scan each row
+// from its end and stop at the first active entry: same bits, far fewer gathers on a wide frontier.
+template <class P, class = void>
+struct is_last_writer : std::false_type {};
+template <class P>
+struct is_last_writer<P, typename std::enable_if<P::gm_last_writer>::type> : std::true_type {};
 // `static const bool gm_fadd32_exact = true;`: T = U = float, process_message is
 // res = message, reduce is a += b and messages are >= 0.  Long rows then use the
 // bit-exact parallel emulation of the serial fp32 fold (k_heavy_fadd32).
@@ -160,6 +170,7 @@ __global__ void __launch_bounds__(256) k_send(prog_bytes<P> pb, int n_pad, const
 // again in the next iteration, so the same pass also produces the next message vector
 // (send_message on the fresh property) and re-arms the active set: one sweep over the vertex
 // properties per iteration instead of three kernels.
+constexpr int GM_APPLY_VPT = 4;  // vertices per thread: all loads of the 4 are issued before any is consumed
 template <class P, class T, class U, class V, bool FUSE>
 __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, int n_pad, const U* __restrict__ y,
                                                const unsigned* __restrict__ ybits, V* __restrict__ vp,
@@ -168,38 +179,51 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
   alignas(16) unsigned char pbuf[sizeof(P)];
   memcpy(pbuf, pb.b, sizeof(P));
   P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  unsigned w = ybits[i >> 5];
-  bool changed = false;
-  if ((w >> (i & 31)) & 1u) {
-    V old = vp[i];
-    V cur = old;
-    prog.P::apply(y[i], cur);
-    changed = (old != cur);
-    vp[i] = cur;
-    if (FUSE) {
+  constexpr int VPT = (sizeof(V) + sizeof(U) <= 32) ? GM_APPLY_VPT : 1;
+  const int base = blockIdx.x * (blockDim.x * VPT) + threadIdx.x;
+  bool got[VPT], touch[VPT];
+  V cur[VPT];
+  U msg[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; k++) {
+    const int i = base + k * 256;
+    got[k] = touch[k] = false;
+    if (i < n_pad) {
+      got[k] = (__ldg(ybits + (i >> 5)) >> (i & 31)) & 1u;
+      touch[k] = got[k] || (FUSE && i < n_valid);
+      if (touch[k]) cur[k] = vp[i];
+      if (got[k]) msg[k] = y[i];
+    }
+  }
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < VPT; k++) {
+    const int i = base + k * 256;
+    bool changed = false;
+    if (got[k]) {
+      V old = cur[k];
+      prog.P::apply(msg[k], cur[k]);
+      changed = (old != cur[k]);
+      vp[i] = cur[k];
+    }
+    if (FUSE && touch[k]) {
       T t;
-      (void)prog.P::send_message(cur, t);
+      (void)prog.P::send_message(cur[k], t);
       x[i] = t;
     }
-  } else if (FUSE && i < n_valid) {
-    T t;
-    (void)prog.P::send_message(vp[i], t);
-    x[i] = t;
-  }
-  unsigned m = __ballot_sync(0xffffffffu, changed);
-  if ((i & 31) == 0) {
-    if (FUSE) {
-      const int lo = i;
-      unsigned all = lo + 32 <= n_valid ? 0xffffffffu : (lo < n_valid ? (1u << (n_valid - lo)) - 1u : 0u);
-      active[i >> 5] = all;  // setAllActive of the next iteration (GraphMatRuntime.h:250-252)
-      xbits[i >> 5] = all;
-    } else {
-      active[i >> 5] = m;  // setAllInactive + set where changed
+    const unsigned m = __ballot_sync(0xffffffffu, changed);
+    if ((threadIdx.x & 31) == 0 && i < n_pad) {
+      if (FUSE) {
+        const unsigned all = i + 32 <= n_valid ? 0xffffffffu : (i < n_valid ? (1u << (n_valid - i)) - 1u : 0u);
+        active[i >> 5] = all;  // setAllActive of the next iteration (GraphMatRuntime.h:250-252)
+        xbits[i >> 5] = all;
+      } else {
+        active[i >> 5] = m;  // setAllInactive + set where changed
+      }
+      any |= (m != 0);
     }
-    if (m && *((volatile int*)flags) == 0) atomicExch(flags, 1);
   }
+  if (any && *((volatile int*)flags) == 0) atomicExch(flags, 1);
 }
 
 __global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
@@ -285,6 +309,68 @@ __global__ void __launch_bounds__(256)
     if (IDENT) {
       if (lane == 0) ybits[slot >> 5] = m;  // heavy and ELL slots never share a word
     } else if (have && len > 0) {
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    }
+  }
+}
+
+// ---------------------------------- SpMSpV: sliced ELL, last-writer programs --
+// Same launch shape as k_sell; every lane walks its row from the END and stops at the first active
+// entry (is_last_writer).  The warp leaves a slice when all its rows are decided.
+template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, bool ACCUM, int UNROLL>
+__global__ void __launch_bounds__(256)
+    k_sell_last(prog_bytes<P> pb, gm_matrix_view M, int slice_begin, int slice_end, int spw, int hot_limit,
+                const T* __restrict__ x, const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
+                unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int* __restrict__ cols = M.s_col;
+  const E* __restrict__ vals = reinterpret_cast<const E*>(M.s_val);
+  int s = slice_begin + warp * spw;
+  const int s_end = min(s + spw, slice_end);
+  for (; s < s_end; s++) {
+    const int slot = M.n_heavy + s * 32 + lane;
+    const int len = __ldg(M.row_len + slot);
+    const long long base = __ldg(M.slice_ptr + s);
+    const int width = __shfl_sync(0xffffffffu, len, 0);
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    bool have = false;
+    if (ACCUM && (IDENT || len > 0)) have = test_bit(ybits, vtx);
+    bool found = false;
+    U acc;
+    const int* cp = cols + base + lane;
+    const E* ep = vals + base + lane;
+    for (int top = width; top > 0; top -= UNROLL) {
+      int c[UNROLL];
+      bool on[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {  // u = 0 is the highest index of the batch
+        const int i = top - 1 - u;
+        on[u] = !found && i >= 0 && i < len;
+        if (on[u]) c[u] = ld_stream(cp + (long long)i * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+        if (on[u]) on[u] = test_bit(xbits, c[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        if (on[u] && !found) {
+          const int i = top - 1 - u;
+          V vprop;
+          if (NEEDVP) vprop = vp[vtx];
+          prog.P::process_message(ld_gather(x, c[u], hot_limit), ld_stream(ep + (long long)i * 32), vprop, acc);
+          found = true;
+        }
+      }
+      if (__ballot_sync(0xffffffffu, !found && len > 0) == 0) break;
+    }
+    if (found) y[vtx] = acc;
+    have = have || found;
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    if (IDENT) {
+      if (lane == 0) ybits[slot >> 5] = m;
+    } else if (found) {
       atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
     }
   }
@@ -514,7 +600,7 @@ __device__ __forceinline__ void warp_ordered_tree(const P& prog, U* wb, U& part,
   }
 }
 
-template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT>
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool LAST = false>
 __global__ void __launch_bounds__(128)
     k_heavy_seg(prog_bytes<P> pb, gm_matrix_view M, int hot_limit, const T* __restrict__ x,
                 const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ partial,
@@ -540,6 +626,30 @@ __global__ void __launch_bounds__(128)
   U part;
   bool pv = false;
   constexpr int UNROLL = sizeof(T) <= 8 ? 8 : 1;
+  if constexpr (LAST) {
+    // last-writer programs: this lane's run from its end, stop at the first active entry
+    for (long long top = iend; top > i && !pv; top -= UNROLL) {
+      int c[UNROLL];
+      bool on[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        on[u] = top - 1 - u >= i;
+        if (on[u]) c[u] = __ldg(cols + top - 1 - u);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+        if (on[u] && !ALLACT) on[u] = test_bit(xbits, c[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        if (on[u] && !pv) {
+          prog.P::process_message(ld_gather(x, c[u], hot_limit), __ldg(vals + top - 1 - u), vprop, part);
+          pv = true;
+        }
+      }
+    }
+    i = iend;
+  }
+  // a lane reads 8 consecutive entries: let L1 keep the sector between the 8 loads
   for (; i < iend; i += UNROLL) {
     int c[UNROLL];
     E ev[UNROLL];
@@ -549,8 +659,8 @@ __global__ void __launch_bounds__(128)
     for (int u = 0; u < UNROLL; u++) {
       on[u] = i + u < iend;
       if (on[u]) {
-        c[u] = ld_stream(cols + i + u);
-        ev[u] = ld_stream(vals + i + u);
+        c[u] = __ldg(cols + i + u);
+        ev[u] = __ldg(vals + i + u);
       }
     }
 #pragma unroll
@@ -777,6 +887,150 @@ namespace gm {
 #ifndef GM_DEFAULT_PASS_HOT
 #define GM_DEFAULT_PASS_HOT 0
 #endif
+
+// ---------------------------------------------- SpMSpV: sparse frontier (push) --
+// The reference's my_spmspv walks only the columns whose x bit is set (spmspv.h:55-63): its work is
+// proportional to the frontier.  These kernels do the same over the column-major companion of the
+// matrix: every entry of an active column becomes a triple (row slot, position in the row's fold
+// order, process_message result); the triples are radix-sorted by (slot, position) and each row's
+// run is folded left to right -- the same order, hence the same bits, as the row-major kernels.
+template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT>
+__global__ void __launch_bounds__(256)
+    k_push_expand(prog_bytes<P> pb, gm_matrix_view M, int n_active, long long n_entries, const int* __restrict__ f_col,
+                  const long long* __restrict__ f_off, const T* __restrict__ x, const V* __restrict__ vp,
+                  unsigned long long* __restrict__ keys, unsigned* __restrict__ order, U* __restrict__ vals) {
+  const P& prog = pb.get();
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  int lo = 0, hi = n_active;  // last k with f_off[k] <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(f_off + mid) <= t) lo = mid; else hi = mid;
+  }
+  const int c = __ldg(f_col + lo);
+  const long long e = __ldg(M.c_ptr + c) + (t - __ldg(f_off + lo));
+  const int slot = __ldg(M.c_row + e);
+  const int rank = __ldg(M.c_rank + e);
+  const E ev = __ldg(reinterpret_cast<const E*>(M.c_val) + e);
+  V vprop;
+  if (NEEDVP) vprop = vp[IDENT ? slot : __ldg(M.slot_vertex + slot)];
+  U out;
+  prog.P::process_message(x[c], ev, vprop, out);
+  vals[t] = out;
+  keys[t] = ((unsigned long long)(unsigned)slot << M.rank_bits) | (unsigned)rank;
+  order[t] = (unsigned)t;
+}
+
+constexpr int GM_PUSH_SHORT_RUN = 16;
+// one thread per sorted triple; the first triple of a row's run folds the run if it is short,
+// else queues it for k_push_fold_long
+template <class P, class U, bool IDENT, bool ACCUM>
+__global__ void __launch_bounds__(256)
+    k_push_fold(prog_bytes<P> pb, gm_matrix_view M, long long n_entries, const unsigned long long* __restrict__ keys,
+                const unsigned* __restrict__ order, const U* __restrict__ vals, U* __restrict__ y,
+                unsigned* __restrict__ ybits, int* __restrict__ n_long, long long* __restrict__ long_runs) {
+  const P& prog = pb.get();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const int rb = M.rank_bits;
+  const unsigned long long slot = __ldg(keys + i) >> rb;
+  if (i > 0 && (__ldg(keys + i - 1) >> rb) == slot) return;
+  // end of the run: first index whose slot is larger
+  long long lo = i, hi = n_entries;  // keys[lo] has this slot, keys[hi] (if any) does not
+  if (i + GM_PUSH_SHORT_RUN < n_entries && (__ldg(keys + i + GM_PUSH_SHORT_RUN) >> rb) == slot) {
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if ((__ldg(keys + mid) >> rb) == slot) lo = mid; else hi = mid;
+    }
+    const int q = atomicAdd(n_long, 1);
+    long_runs[2 * q] = i;
+    long_runs[2 * q + 1] = hi;
+    return;
+  }
+  const int vtx = IDENT ? (int)slot : __ldg(M.slot_vertex + (int)slot);
+  U acc;
+  bool have = false;
+  if (ACCUM && ((__ldg(ybits + (vtx >> 5)) >> (vtx & 31)) & 1u)) {
+    acc = y[vtx];
+    have = true;
+  }
+  for (long long j = i; j < n_entries && j <= i + GM_PUSH_SHORT_RUN; j++) {
+    if (j > i && (__ldg(keys + j) >> rb) != slot) break;
+    const U v = vals[__ldg(order + j)];
+    if (have) prog.P::reduce_function(acc, v);
+    else { acc = v; have = true; }
+  }
+  y[vtx] = acc;
+  atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+}
+
+// one warp per long run.  REORDER (associative reduce): every lane folds a contiguous chunk in
+// order, the 32 partials are folded in lane order.  Otherwise 32 values are loaded at a time and
+// folded one by one (exact for any reduce_function).
+template <class P, class U, bool IDENT, bool ACCUM, bool REORDER>
+__global__ void __launch_bounds__(128)
+    k_push_fold_long(prog_bytes<P> pb, gm_matrix_view M, const int* __restrict__ n_long,
+                     const long long* __restrict__ long_runs, const unsigned long long* __restrict__ keys,
+                     const unsigned* __restrict__ order, const U* __restrict__ vals, U* __restrict__ y,
+                     unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  extern __shared__ __align__(16) unsigned char push_sm[];
+  U* stage = reinterpret_cast<U*>(push_sm) + (threadIdx.x >> 5) * 32;
+  const int lane = threadIdx.x & 31;
+  const int nq = *n_long;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += (gridDim.x * blockDim.x) >> 5) {
+    const long long b = long_runs[2 * q], e = long_runs[2 * q + 1];
+    const int slot = (int)(__ldg(keys + b) >> M.rank_bits);
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    U acc;
+    bool have = false;
+    if (ACCUM && ((__ldg(ybits + (vtx >> 5)) >> (vtx & 31)) & 1u)) {
+      acc = y[vtx];
+      have = true;
+    }
+    if (REORDER) {
+      const long long chunk = (e - b + 31) / 32;
+      const long long cb = b + lane * chunk, ce = cb + chunk < e ? cb + chunk : e;
+      U part;
+      bool hp = false;
+      for (long long j = cb; j < ce; j++) {
+        const U v = vals[__ldg(order + j)];
+        if (hp) prog.P::reduce_function(part, v);
+        else { part = v; hp = true; }
+      }
+      stage[lane] = part;
+      const unsigned hm = __ballot_sync(0xffffffffu, hp);
+      __syncwarp();
+      if (lane == 0) {
+        for (int k = 0; k < 32; k++) {
+          if (!((hm >> k) & 1u)) continue;
+          if (have) prog.P::reduce_function(acc, stage[k]);
+          else { acc = stage[k]; have = true; }
+        }
+      }
+      __syncwarp();
+    } else {
+      for (long long j0 = b; j0 < e; j0 += 32) {
+        const bool on = j0 + lane < e;
+        if (on) stage[lane] = vals[__ldg(order + j0 + lane)];
+        __syncwarp();
+        if (lane == 0) {
+          const int cnt = e - j0 < 32 ? (int)(e - j0) : 32;
+          for (int k = 0; k < cnt; k++) {
+            if (have) prog.P::reduce_function(acc, stage[k]);
+            else { acc = stage[k]; have = true; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0 && have) {
+      y[vtx] = acc;
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    }
+  }
+}
+
 inline int gm_sm_count() {
   static int n = 0;
   if (!n) {
@@ -791,6 +1045,8 @@ inline int gm_sm_count() {
 struct step_counters {
   long long launches = 0;
   long long edges = 0;
+  long long push_passes = 0;
+  long long last_frontier_cols = -1, last_frontier_entries = -1;  // of the latest sparse pass (trace only)
 };
 
 template <class P>
@@ -852,7 +1108,8 @@ struct engine {
         U* partial = (U*)scratch;
         unsigned char* pvalid = (unsigned char*)scratch + pbytes;
         const size_t sh = 4 * 32 * sizeof(U);
-        k_heavy_seg<P, T, U, V, E, ALLACT, NEEDVP, IDENT><<<(M.n_segs + 3) / 4, 128, sh, st>>>(pb, M, hot, x, xbits, vp, partial, pvalid);
+        constexpr bool LASTW = is_last_writer<P>::value && !ALLACT;
+        k_heavy_seg<P, T, U, V, E, ALLACT, NEEDVP, IDENT, LASTW><<<(M.n_segs + 3) / 4, 128, sh, st>>>(pb, M, hot, x, xbits, vp, partial, pvalid);
         k_heavy_combine<P, U, IDENT, ACCUM><<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, partial, pvalid, y, ybits);
         if (sc) sc->launches += 2;
       }
@@ -899,6 +1156,45 @@ struct engine {
         return 0;
       }
     }
+    // sparse frontier: walk only the active columns when they hold few entries (push, see k_push_expand)
+    if constexpr (!ALLACT && sizeof(U) <= 16 && sizeof(E) == 4) {
+      const int push_div = gv.push_divisor;  // 0: never
+      const long long push_min = gv.push_min_nnz;
+      if (push_div > 0 && M.nnz >= push_min && gv.owner) {
+        const int which = (&M == &gv.A) ? 0 : 1;
+        int n_act = 0;
+        long long n_ent = 0;
+        if (gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+        if (sc) { sc->last_frontier_cols = n_act; sc->last_frontier_entries = n_ent; }
+        if (n_ent * push_div <= M.nnz) {
+          if (n_ent == 0) {  // nothing arrives: y stays cleared
+            if (sc) sc->push_passes++;
+            return 0;
+          }
+          gm_graph_view gv2;
+          if (gm_graph_view_get(gv.owner, &gv2)) return 1;  // the companion may just have been built
+          const gm_matrix_view& MP = which == 0 ? gv2.A : gv2.AT;
+          gm_push_plan plan;
+          if (gm_push_prepare(gv.owner, which, vecs, n_act, n_ent, &plan)) return 1;
+          const unsigned blocks = (unsigned)((n_ent + 255) / 256);
+          k_push_expand<P, T, U, V, E, NEEDVP, IDENT><<<blocks, 256, 0, st>>>(pb, MP, n_act, n_ent, plan.f_col, plan.f_off, x, vp,
+                                                                              plan.keys, plan.order, (U*)plan.vals);
+          if (gm_push_sort(gv.owner, &plan)) return 1;
+          // the long-run queue reuses the spare key buffer (at most n_ent / 17 runs of 2 entries each)
+          int* n_long = gv.d_flags + 13;
+          long long* long_runs = reinterpret_cast<long long*>(plan.keys_alt);
+          GM_CUDA_OK(cudaMemsetAsync(n_long, 0, sizeof(int), st));
+          k_push_fold<P, U, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, MP, n_ent, plan.keys, plan.order, (const U*)plan.vals, y,
+                                                                  vv.y_bits, n_long, long_runs);
+          const int lb = gm_sm_count() * 4;
+          k_push_fold_long<P, U, IDENT, ACCUM, REORDER><<<lb, 128, 4 * 32 * sizeof(U), st>>>(
+              pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y, vv.y_bits);
+          if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; }
+          GM_CUDA_OK(cudaGetLastError());
+          return 0;
+        }
+      }
+    }
     // heavy rows and sliced-ELL rows are disjoint: run them concurrently on two streams
     cudaStream_t sh = gv.aux_stream ? (cudaStream_t)gv.aux_stream : st;
     const bool fork = M.n_heavy > 0 && M.n_slices > 0 && sh != st;
@@ -917,15 +1213,24 @@ struct engine {
       constexpr int UN = (sizeof(T) <= 8 && sizeof(U) <= 8) ? 8 : 1;
       static const int spw_tail = getenv("GM_SELL_SPW") ? atoi(getenv("GM_SELL_SPW")) : 8;
       const int nw = M.n_slices_wide < M.n_slices ? M.n_slices_wide : M.n_slices;
+      constexpr bool LASTW = is_last_writer<P>::value && !ALLACT && sizeof(T) <= 8 && sizeof(U) <= 8;
       if (nw > 0) {
-        k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW><<<(nw + 7) / 8, 256, 0, st>>>(
-            pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        if constexpr (LASTW)
+          k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(nw + 7) / 8, 256, 0, st>>>(
+              pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        else
+          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW><<<(nw + 7) / 8, 256, 0, st>>>(
+              pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
         if (sc) sc->launches++;
       }
       if (M.n_slices > nw) {
         const int warps = (M.n_slices - nw + spw_tail - 1) / spw_tail;
-        k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN><<<(warps + 7) / 8, 256, 0, st>>>(
-            pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        if constexpr (LASTW)
+          k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(warps + 7) / 8, 256, 0, st>>>(
+              pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
+        else
+          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN><<<(warps + 7) / 8, 256, 0, st>>>(
+              pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
         if (sc) sc->launches++;
       }
     }
@@ -980,6 +1285,10 @@ struct engine {
   static constexpr bool NO_HOOK =
       std::is_same<decltype(&P::do_every_iteration), void (GraphMat::GraphProgram<T, U, V, E>::*)(int)>::value;
 
+  static int apply_blocks(int n) {
+    constexpr int per = 256 * ((sizeof(V) + sizeof(U) <= 32) ? GM_APPLY_VPT : 1);
+    return (n + per - 1) / per;
+  }
   // the apply loop   GraphMatRuntime.h:184-226 (flag = !converged)
   static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc, bool fuse_send = false) {
     cudaStream_t st = (cudaStream_t)gv.stream;
@@ -987,10 +1296,10 @@ struct engine {
     T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
     unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
     if (fuse_send)
-      k_apply<P, T, U, V, true><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
+      k_apply<P, T, U, V, true><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
                                                                 (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
     else
-      k_apply<P, T, U, V, false><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
+      k_apply<P, T, U, V, false><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
                                                                  (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
     if (sc) sc->launches++;
     GM_CUDA_OK(cudaGetLastError());
@@ -1031,30 +1340,77 @@ struct engine {
     GM_CUDA_OK(cudaEventRecord(e0, st));
     if (all && set_all_active(gv, &sc)) return 1;
     int it = 0, converged = 1;
+    // Fixed iteration count and no do_every_iteration hook: nothing on the host depends on the
+    // "changed" flag between iterations (GraphMatRuntime.h:254-260 tests it only when
+    // iterations <= 0), so the whole run is enqueued without a host round trip per iteration and
+    // the flag of the last iteration is read once at the end.
+    const bool async = iterations > 0 && NO_HOOK && !getenv("GM_SYNC_LOOP");
+    constexpr int EV_BATCH = 64;
+    std::vector<cudaEvent_t> evs;
+    const bool timing = stats != nullptr;
+    auto harvest = [&](int count) -> int {
+      if (count <= 0) return 0;
+      GM_CUDA_OK(cudaEventSynchronize(evs[2 * (count - 1) + 1]));
+      for (int k = 0; k < count; k++) {
+        float t;
+        GM_CUDA_OK(cudaEventElapsedTime(&t, evs[2 * k], evs[2 * k + 1]));
+        ms_spmv += t;
+      }
+      return 0;
+    };
+    if (async && timing) {
+      evs.resize(2 * (size_t)std::min(iterations, EV_BATCH));
+      for (auto& e : evs) GM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDefault));
+    }
+    int pending = 0;
     while (1) {
       GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
       if (!(fuse && it > 0) && send(prog, gv, vv, &sc)) return 1;  // fused: the previous apply already sent
       if (gv.world > 1 && gm_graph_exchange_x(g, tmp)) return 1;
-      const bool timing = stats != nullptr;
-      if (timing) GM_CUDA_OK(cudaEventRecord(s0, st));
-      if (spmspv(prog, gv, vv, all, &sc, tmp)) return 1;
-      if (timing) GM_CUDA_OK(cudaEventRecord(s1, st));
-      if (apply(prog, gv, vv, &sc, fuse)) return 1;
-      GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-      GM_CUDA_OK(cudaStreamSynchronize(st));
-      int changed = gv.h_flags[0];
-      if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
-      converged = !changed;
-      if (timing) {
-        float t;
-        GM_CUDA_OK(cudaEventElapsedTime(&t, s0, s1));
-        ms_spmv += t;
+      cudaEvent_t es0 = s0, es1 = s1;
+      if (async && timing) {
+        es0 = evs[2 * pending];
+        es1 = evs[2 * pending + 1];
       }
-      prog.do_every_iteration(it);
+      if (timing) GM_CUDA_OK(cudaEventRecord(es0, st));
+      if (spmspv(prog, gv, vv, all, &sc, tmp)) return 1;
+      if (timing) GM_CUDA_OK(cudaEventRecord(es1, st));
+      if (apply(prog, gv, vv, &sc, fuse)) return 1;
+      if (async) {
+        if (timing && ++pending == EV_BATCH) {
+          if (harvest(pending)) return 1;
+          pending = 0;
+        }
+      } else {
+        GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GM_CUDA_OK(cudaStreamSynchronize(st));
+        int changed = gv.h_flags[0];
+        if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
+        converged = !changed;
+        if (timing) {
+          float t;
+          GM_CUDA_OK(cudaEventElapsedTime(&t, s0, s1));
+          ms_spmv += t;
+          static const bool trace = getenv("GM_TRACE_ITERS") != nullptr;
+          if (trace)
+            fprintf(stderr, "graphmat_b200: iteration %d: SpMSpV %.3f ms, frontier %lld columns / %lld entries, push passes so far %lld\n",
+                    it, t, sc.last_frontier_cols, sc.last_frontier_entries, sc.push_passes);
+        }
+        prog.do_every_iteration(it);
+      }
       if (all && !fuse && set_all_active(gv, &sc)) return 1;
       it++;
       if (it == iterations) break;
       if (iterations <= 0 && converged) break;
+    }
+    if (async) {
+      GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (timing && harvest(pending)) return 1;
+      GM_CUDA_OK(cudaStreamSynchronize(st));
+      int changed = gv.h_flags[0];
+      if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
+      converged = !changed;
+      for (auto& e : evs) cudaEventDestroy(e);
     }
     GM_CUDA_OK(cudaEventRecord(e1, st));
     GM_CUDA_OK(cudaEventSynchronize(e1));
@@ -1067,6 +1423,7 @@ struct engine {
       stats->ms_spmv = ms_spmv;
       stats->kernel_launches = sc.launches;
       stats->edges_processed = sc.edges;
+      stats->push_passes = sc.push_passes;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

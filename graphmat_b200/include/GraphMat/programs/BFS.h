@@ -24,6 +24,7 @@ class BFS2 : public GraphMat::GraphProgram<unsigned long long int, unsigned long
  public:
   gm_bfs::depth_type current_depth;
   static const bool gm_reorderable = true;  // a = b keeps the LAST contribution: associative, order kept
+  static const bool gm_last_writer = true;  // ... so a sparse pass may scan each row from its end (gm_engine.cuh)
 
   GM_HD BFS2() {
     current_depth = 1;

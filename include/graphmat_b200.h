@@ -65,6 +65,13 @@ typedef struct gm_matrix_view {
   int n_segs, seg_len;          /* heavy rows cut into segments of seg_len entries (associative programs) */
   const int* seg_ptr;           /* n_heavy + 1: first segment of each heavy row */
   const int* seg_row;           /* n_segs: heavy row of each segment */
+  /* column-major companion for sparse frontiers (NULL until gm_graph_push_ready): the reference's
+   * DCSC walks only the ACTIVE columns (include/GMDP/singlenode/spmspv.h:55-63); so does the push path */
+  const long long* c_ptr;       /* n_full + 1: entries of x index c are [c_ptr[c], c_ptr[c+1]) */
+  const int* c_row;             /* row slot per entry */
+  const int* c_rank;            /* position of the entry in its row's fold order (ascending native column) */
+  const void* c_val;            /* edge value per entry */
+  int rank_bits;                /* c_rank < 2^rank_bits */
 } gm_matrix_view;
 
 typedef struct gm_graph_view {
@@ -80,6 +87,9 @@ typedef struct gm_graph_view {
   void* aux_stream;             /* second stream: heavy rows run beside the sliced-ELL rows */
   void* ev_fork; void* ev_join; /* cudaEvent_t pair ordering the two streams */
   int hot_limit;                /* x indices below this are gathered with an L1-resident hint */
+  gm_graph* owner;              /* the handle this view was taken from */
+  int push_divisor;             /* sparse-frontier path when frontier entries * divisor <= nnz; 0 = never */
+  long long push_min_nnz;       /* ... and the matrix holds at least this many entries */
 } gm_graph_view;
 
 typedef struct gm_vectors_view {
@@ -95,6 +105,7 @@ typedef struct gm_run_stats {
   float ms_spmv;         /* device time inside the SpMSpV kernels */
   long long kernel_launches;
   long long edges_processed; /* matrix entries swept */
+  long long push_passes;     /* SpMSpV passes that took the sparse-frontier (push) path */
 } gm_run_stats;
 
 const char* gm_last_error(void);
@@ -146,6 +157,28 @@ typedef int (*gm_allreduce_or_fn)(void* ctx, int* host_flag);
 int gm_graph_set_exchange(gm_graph* g, gm_allgather_fn allgather, gm_allreduce_or_fn allreduce_or, void* ctx);
 int gm_graph_exchange_x(gm_graph* g, gm_vectors* v);     /* all-gather x values + bit words in place */
 int gm_graph_allreduce_or(gm_graph* g, int* flag);       /* "some vertex changed" across ranks */
+
+/* ---- sparse frontiers: push SpMSpV over the active columns only.  The reference's my_spmspv visits only
+ *      columns whose x bit is set (include/GMDP/singlenode/spmspv.h:55-63), so its work is proportional to
+ *      the frontier; the row-major kernels sweep every entry.  For ACTIVE_ONLY programs the engine counts the
+ *      frontier's entries each iteration and, when they are few, expands them into (row, fold position, value)
+ *      triples, sorts the triples and folds each row in the reference's order.  which: 0 = A, 1 = AT. */
+typedef struct gm_push_plan {
+  int n_active;               /* active columns with at least one owned entry */
+  long long n_entries;        /* entries of those columns */
+  int* f_col;                 /* device, n_active: active x indices */
+  long long* f_off;           /* device, n_active + 1: first triple of each active column */
+  unsigned long long* keys;   /* device, n_entries: (row slot << rank_bits) | fold position */
+  unsigned int* order;        /* device, n_entries: index into vals */
+  void* vals;                 /* device, n_entries * sizeof_U: process_message results */
+  unsigned long long* keys_alt; unsigned int* order_alt; void* sort_tmp; long long sort_tmp_bytes; /* sort buffers */
+  int key_bits;
+} gm_push_plan;
+int gm_graph_push_ready(gm_graph* g, int which);   /* build the column-major companion (idempotent) */
+int gm_graph_set_push_policy(gm_graph* g, int divisor, long long min_nnz); /* defaults 16, 2^18; divisor 0 = never push */
+int gm_push_count(gm_graph* g, int which, const gm_vectors* v, int* n_active, long long* n_entries); /* blocking */
+int gm_push_prepare(gm_graph* g, int which, gm_vectors* v, int n_active, long long n_entries, gm_push_plan* plan);
+int gm_push_sort(gm_graph* g, gm_push_plan* plan);  /* sorts (keys, order) by key; keys/order point at the result */
 
 /* ---- the five vertex programs BASELINE.json names, compiled into the library ----
  * run == run_graph_program(&program, G, iterations, &tmp) (include/GraphMatRuntime.h:93-279).

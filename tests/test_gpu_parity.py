@@ -206,3 +206,82 @@ def test_properties_at_scale():
     assert (key[np.minimum(pos, len(key) - 1)] == q).all()
     # no edge skips a level
     assert (depth[d - 1][vis[s - 1]] <= depth[s - 1][vis[s - 1]] + 1).all()
+
+
+# ---- sparse-frontier (push) path: every SpMSpV pass forced through it must still equal the oracle ----
+def _bfs_run(Gb, src0):
+    n = Gb.nvertices
+    vp = np.zeros(n, capi.BFS_DTYPE)
+    vp["depth"] = 0xFFFFFFFF
+    vp["parent"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    vp["id"] = np.arange(1, n + 1, dtype=np.uint64)
+    vp["depth"][src0 - 1] = 0
+    Gb.set_vertexproperties(vp)
+    Gb.set_all_inactive()
+    Gb.set_active(src0)
+    st = Gb.run(capi.PROG_BFS, capi.BFSState(1), capi.UNTIL_CONVERGENCE)
+    out = Gb.get_vertexproperties()
+    return out["depth"].copy(), out["parent"].copy(), st
+
+
+def _sssp_run(Gs, src0):
+    inf = np.zeros(1, capi.SSSP_DTYPE)
+    inf["distance"] = 0xFFFFFFFF
+    Gs.set_all_vertexproperty(inf[0])
+    Gs.set_all_inactive()
+    Gs.set_vertexproperty(src0, np.zeros(1, capi.SSSP_DTYPE)[0])
+    Gs.set_active(src0)
+    st = Gs.run(capi.PROG_SSSP, None, capi.UNTIL_CONVERGENCE)
+    return Gs.get_vertexproperties()["distance"].copy(), st
+
+
+@pytest.mark.parametrize("case", ["rmat12", "rmat14_heavy16", "random", "test_mtx"])
+def test_push_path_forced(case):
+    t = 4
+    heavy = 0
+    if case == "rmat12":
+        n, s, d, v = util.rmat_numpy(12, weight_max=127)
+    elif case == "rmat14_heavy16":
+        n, s, d, v = capi.rmat_edges(14, 16, seed=3, weight_max=127)
+        heavy = 16
+    elif case == "random":
+        n = 3000
+        s, d, v = util.random_graph(n, 50000, 31, weight_max=50)
+    else:
+        m = util.TEST_MTX
+        n, s, d, v = m["n"], m["src"], m["dst"], m["val"]
+    src0 = util.first_source(s)
+    od, op, oit, _ = port.bfs(n, s, d, src0, threads=t)
+    Gb = capi.Graph.from_edges(n, s, d, None, capi.BFS_DTYPE, threads=t, heavy_threshold=heavy)
+    Gb.set_push_policy(1, 0)            # frontier entries <= nnz always holds: every pass is a push pass
+    depth, parent, st = _bfs_run(Gb, src0)
+    assert st.push_passes == st.iterations == oit
+    assert (depth == od).all() and (parent == op).all()
+    Gb.set_push_policy(0, 0)            # never push: the row-major kernels
+    depth, parent, st = _bfs_run(Gb, src0)
+    assert st.push_passes == 0 and (depth == od).all() and (parent == op).all()
+    odist, osit, _ = port.sssp(n, s, d, v, src0, threads=t)
+    Gs = capi.Graph.from_edges(n, s, d, v, capi.SSSP_DTYPE, threads=t, heavy_threshold=heavy)
+    Gs.set_push_policy(1, 0)
+    dist, st = _sssp_run(Gs, src0)
+    assert st.push_passes == st.iterations == osit
+    assert (dist == odist).all()
+    Gs.set_push_policy(4, 0)            # mixed: push while the frontier holds <= 1/4 of the entries
+    dist, st = _sssp_run(Gs, src0)
+    assert (dist == odist).all() and st.iterations == osit
+
+
+def test_push_path_default_policy_rmat18():
+    """default policy on a graph large enough to use it: some passes push, some sweep; results as the oracle"""
+    n, s, d, v = capi.rmat_edges(18, 16, seed=1, weight_max=127)
+    src0 = util.first_source(s)
+    Gb = capi.Graph.rmat(18, capi.BFS_DTYPE, seed=1, threads=4, build_mask=2)
+    Gb.push_ready(1)
+    depth, parent, st = _bfs_run(Gb, src0)
+    od, op, oit, _ = port.bfs(n, s, d, src0, threads=4)
+    assert 0 < st.push_passes < st.iterations == oit
+    assert (depth == od).all() and (parent == op).all()
+    Gs = capi.Graph.from_edges(n, s, d, v, capi.SSSP_DTYPE, threads=4, build_mask=2)
+    dist, st = _sssp_run(Gs, src0)
+    odist, osit, _ = port.sssp(n, s, d, v, src0, threads=4)
+    assert st.push_passes > 0 and st.iterations == osit and (dist == odist).all()
