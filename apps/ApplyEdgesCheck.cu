@@ -1,0 +1,81 @@
+// ApplyEdgesCheck: the reference's test/test_apply_edges.cpp:38-63 (Graph::applyToAllEdges followed by
+// getEdgelist) on the device engine, plus a check that the DEVICE matrices carry the new values:
+// SSSP over the rewritten weights must equal a host Bellman-Ford over the same weights.
+// usage: ApplyEdgesCheck <N>      prints "apply_edges ok" on success
+#include <algorithm>
+#include <vector>
+
+#include "GraphMatRuntime.h"
+#include "GraphMat/programs/SSSP.h"
+#include "common.h"
+
+// src_vp.distance doubles as the "vertex id" payload of the reference test (V = int there)
+void apply_edges_fn(int* edge_val, const SSSP_vertex_type& src_vp, const SSSP_vertex_type& dst_vp, void* vsp) {
+  int s = *(int*)vsp;
+  *edge_val = (int)src_vp.distance + s * (int)dst_vp.distance;
+}
+
+static unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+
+int check(GraphMat::edgelist_t<int> E) {
+  GraphMat::Graph<SSSP_vertex_type, int> G;
+  G.ReadEdgelist(E);
+  const int n = G.getNumberOfVertices();
+  for (int i = 1; i <= n; i++) {
+    SSSP_vertex_type v;
+    v.distance = i;
+    G.setVertexproperty(i, v);
+  }
+  int s = 2;
+  G.applyToAllEdges(apply_edges_fn, (void*)&s);
+  GraphMat::edgelist_t<int> E2;
+  G.getEdgelist(E2);
+  if (E2.nnz != E.nnz) return 1;
+  for (int i = 0; i < E2.nnz; i++)
+    if (E2.edges[i].val != E2.edges[i].src + s * E2.edges[i].dst) return 2;  // test_apply_edges.cpp:62-65
+  // the device matrices: SSSP from vertex 1 over the new weights vs host Bellman-Ford
+  SSSP_vertex_type inf, zero;
+  zero.distance = 0;
+  G.setAllVertexproperty(inf);
+  G.setAllInactive();
+  G.setVertexproperty(1, zero);
+  G.setActive(1);
+  SSSP<int> prog;
+  GraphMat::run_graph_program(&prog, G, GraphMat::UNTIL_CONVERGENCE);
+  std::vector<unsigned> dist(n + 1, gm_sssp::kMaxDist);
+  dist[1] = 0;
+  for (int it = 0; it < n; it++) {
+    bool ch = false;
+    for (int i = 0; i < E2.nnz; i++) {
+      const auto& e = E2.edges[i];
+      if (dist[e.src] != gm_sssp::kMaxDist && dist[e.src] + (unsigned)e.val < dist[e.dst]) {
+        dist[e.dst] = dist[e.src] + (unsigned)e.val;
+        ch = true;
+      }
+    }
+    if (!ch) break;
+  }
+  for (int i = 1; i <= n; i++)
+    if (G.getVertexproperty(i).distance != dist[i]) return 3;
+  E2.clear();
+  return 0;
+}
+
+int main(int argc, char* argv[]) {
+  const int N = argc > 1 ? atoi(argv[1]) : 500;
+  // generate_identity_edgelist / generate_random_edgelist of test/generator.h
+  GraphMat::edgelist_t<int> I(N, N, N);
+  for (int i = 0; i < N; i++) I.edges[i] = GraphMat::edge_t<int>(i + 1, i + 1, 1);
+  int rc = check(I);
+  if (rc) { printf("apply_edges identity FAILED (%d)\n", rc); return 1; }
+  I.clear();
+  const int nnz = N * 16;
+  GraphMat::edgelist_t<int> R(N, N, nnz);
+  unsigned seed = 7;
+  for (int i = 0; i < nnz; i++) R.edges[i] = GraphMat::edge_t<int>(1 + lcg(seed) % N, 1 + lcg(seed) % N, 1 + lcg(seed) % 9);
+  rc = check(R);
+  if (rc) { printf("apply_edges random FAILED (%d)\n", rc); return 1; }
+  R.clear();
+  printf("apply_edges ok\n");
+  return 0;
+}

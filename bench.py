@@ -47,6 +47,17 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(scale, world):
+    """DRAM bytes of one SpMSpV pass from the committed ncu --set full capture (profiles/), same workload only."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_pagerank_rmat26.json")))
+        if scale == 26 and world == 1:
+            return float(t["dram_bytes_per_pass"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -227,6 +238,7 @@ def main():
     if not args.no_bfs and world == 1:
         from graphmat_b200 import apps
         Gb = capi.Graph.rmat(22, capi.BFS_DTYPE, seed=1, threads=args.threads, build_mask=2)
+        Gb.push_ready(1)  # column-major companion of the sparse-frontier path: graph construction, not BFS time
         src0 = Gb.first_source()
         nb = Gb.nvertices
         vp = np.zeros(nb, capi.BFS_DTYPE)
@@ -243,7 +255,8 @@ def main():
             best = stb.ms_total if best is None else min(best, stb.ms_total)
         reach = int(Gb.reduce(capi.REDUCE_REACHABLE))
         bfs = {"workload": "BFS RMAT scale-22", "gteps": Gb.nnz / (best * 1e-3) / 1e9, "ms": best,
-               "iterations": stb.iterations, "reachable": reach, "source": src0}
+               "iterations": stb.iterations, "reachable": reach, "source": src0,
+               "push_passes": int(stb.push_passes), "entries_swept": int(stb.edges_processed)}
         Gb.close()
 
     if rank == 0:
@@ -251,6 +264,7 @@ def main():
         # algorithmic bytes per SpMSpV pass: nnz*(sizeof(E)+sizeof(idx)) + |active|*sizeof(M)
         alg_bytes = nnz * (4 + 4) + n * 4
         ms_per_pass = spmv_ms / passes
+        traffic, traffic_src = measured_traffic(args.scale, world)
         achieved = alg_bytes / world / (ms_per_pass * 1e-3) / 1e9  # per GPU
         line = {
             "metric": "GTEPS (PageRank, nnz*iterations/time of run_graph_program)", "value": gteps, "unit": "GTEPS",
@@ -266,7 +280,7 @@ def main():
                     "d2h_bytes_per_step": n * vdt.itemsize, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "SpMSpV pass (k_heavy + k_sell)", "ms_per_launch": ms_per_pass,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "SpMSpV pass (k_heavy + k_sell)", "ms_per_launch": ms_per_pass,
                          "algorithmic_bytes": alg_bytes // world, "peak_source": peak_src,
                          "spmv_share_of_step": spmv_ms / dev_ms},
             "clocks": sampler.summary(),

@@ -97,7 +97,7 @@ SYMBOLS = [
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
     "gm_debug_fold_f32_device", "gm_graph_push_ready", "gm_graph_set_push_policy", "gm_push_count", "gm_push_prepare",
-    "gm_push_sort",
+    "gm_push_sort", "gm_graph_set_edge_values",
 ]
 
 
@@ -256,6 +256,12 @@ class Graph:
     def share_vertexproperty(self, owner):
         _check(lib().gm_graph_share_vertexproperty(self.h, owner.h), "gm_graph_share_vertexproperty")
         self._keep.append(owner)
+
+    def set_edge_values(self, src, dst, val):
+        """Graph::applyToAllEdges, host-evaluated: new value of every edge (same src/dst as at creation)."""
+        src, dst, val = _i32(src), _i32(dst), _i32(val)
+        _check(lib().gm_graph_set_edge_values(self.h, C.c_longlong(len(src)), _p(src), _p(dst), _p(val)),
+               "gm_graph_set_edge_values")
 
     def push_ready(self, which=1):
         """Build the column-major companion used for sparse frontiers (0 = A, 1 = AT) ahead of the first run."""

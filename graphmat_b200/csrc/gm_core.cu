@@ -614,6 +614,47 @@ extern "C" int gm_graph_create(gm_graph** out, int nvertices, long long nnz, con
   return 0;
 }
 
+// Graph::applyToAllEdges (include/Graph.h:389-402) rewrites every stored edge value in both operand
+// matrices.  The per-edge function is host code in the reference's signature, so the host side
+// evaluates it and hands the new values over with the edge list; the matrices are rebuilt in place
+// (same placement, same row order, same fold order) while vertex properties and the active set stay.
+extern "C" int gm_graph_set_edge_values(gm_graph* g, long long nnz, const int* src, const int* dst, const void* val) {
+  if (nnz != g->nnz) {
+    gm_set_error("gm_graph_set_edge_values: nnz differs from the graph's");
+    return 1;
+  }
+  cudaStream_t st = g->stream;
+  CK(cudaStreamSynchronize(st));
+  if (g->aux_stream) CK(cudaStreamSynchronize(g->aux_stream));
+  const bool hasA = g->A.n_slots > 0, hasAT = g->AT.n_slots > 0;
+  const bool identA = g->A.identity != 0, identAT = g->AT.identity != 0;
+  int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
+  if (dalloc(&d_src, nnz) || dalloc(&d_dst, nnz) || dalloc(&d_val, nnz)) return 1;
+  if (nnz) {
+    CK(cudaMemcpyAsync(d_src, src, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dst, dst, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    const int npart = g->ref_threads * 16;
+    k_to_native<<<nblk(nnz), 256, 0, st>>>(d_src, nnz, g->n, npart);
+    k_to_native<<<nblk(nnz), 256, 0, st>>>(d_dst, nnz, g->n, npart);
+  }
+  int rc = 0;
+  if (hasAT) {
+    matrix_free(g->AT);
+    g->AT = gm_matrix();
+    rc = build_matrix<int>(g, g->AT, d_dst, d_src, d_val, nnz, identAT);
+  }
+  if (!rc && hasA) {
+    matrix_free(g->A);
+    g->A = gm_matrix();
+    rc = build_matrix<int>(g, g->A, d_src, d_dst, d_val, nnz, identA);
+  }
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  cudaFree(d_val);
+  return rc;
+}
+
 extern "C" int gm_graph_create_rmat(gm_graph** out, int scale, int edge_factor, unsigned long long seed, int weight_max,
                                     unsigned long long weight_seed, int sizeof_V, const gm_graph_opts* opts) {
   *out = nullptr;

@@ -6,9 +6,9 @@
 // so they cost O(1) each instead of one PCIe round trip each.
 //
 // Differences a maintainer should know: E must be a 4-byte type; the
-// GraphMat-binary snapshot format (ReadGraphMatBin / WriteGraphMatBin, Boost archives) and
-// applyToAllEdges are outside this hot-path build and print-and-exit like the reference's
-// error convention.
+// GraphMat-binary snapshot format (ReadGraphMatBin / WriteGraphMatBin, Boost archives) is
+// outside this hot-path build and prints-and-exits like the reference's error convention;
+// applyToAllEdges evaluates its (host) function on the host and refills the device matrices.
 #ifndef GRAPHMAT_B200_GRAPH_H
 #define GRAPHMAT_B200_GRAPH_H
 #include <cstdio>
@@ -201,7 +201,17 @@ class Graph {
       else { T a = *val; ReduceFn(a, t, val, param); }
     }
   }
-  void applyToAllEdges(void (*)(E*, const V&, const V&, void*), void* = nullptr) { unsupported("applyToAllEdges"); }
+  // Graph.h:389-402 / GMDP/singlenode/applyedges.h:38-76: ApplyFn(&edge, vp[src], vp[dst], param) for every
+  // edge, on both A and AT.  ApplyFn is host code (the reference's signature), so it is evaluated here
+  // on the host mirror and the device matrices are refilled in place (gm_graph_set_edge_values).
+  void applyToAllEdges(void (*ApplyFn)(E*, const V&, const V&, void*), void* param = nullptr) {
+    pull();
+    for (long long i = 0; i < nnz; i++)
+      ApplyFn(&e_val[i], mirror->host[e_src[i] - 1], mirror->host[e_dst[i] - 1], param);
+    push();
+    detail::check(gm_graph_set_edge_values(handle, nnz, e_src.data(), e_dst.data(), e_val.data()),
+                  "gm_graph_set_edge_values");
+  }
 
   // ---- used by run_graph_program ----
   void push() {  // host writes -> device

@@ -125,6 +125,10 @@ int gm_graph_create_rmat(gm_graph** out, int scale, int edge_factor, unsigned lo
 int gm_rmat_edges_host(int scale, int edge_factor, unsigned long long seed, int weight_max,
                        unsigned long long weight_seed, int* src, int* dst, int* val);
 int gm_graph_destroy(gm_graph* g);
+/* Graph::applyToAllEdges (include/Graph.h:389-402; GMDP/singlenode/applyedges.h:38-76): new value of every edge,
+ * in the order and with the (src, dst) the graph was created from (host arrays).  Both operand matrices are
+ * refilled in place; vertex properties, the active set and the vertex placement are kept. */
+int gm_graph_set_edge_values(gm_graph* g, long long nnz, const int* src, const int* dst, const void* val);
 int gm_graph_view_get(const gm_graph* g, gm_graph_view* out);
 int gm_graph_synchronize(const gm_graph* g);
 

@@ -35,10 +35,11 @@ if "bfs22" in what or "bfs24" in what:
         sc, st.iterations, st.ms_total, st.ms_spmv, G.nnz / st.ms_total / 1e6, st.kernel_launches))
     G.close()
 
-if "sssp22" in what or "ds22" in what:
-    n, s, d, v = capi.rmat_edges(22, 16, seed=1, weight_max=127, weight_seed=2)
+if "sssp22" in what or "ds22" in what or "sssp24" in what or "ds24" in what:
+    sc = 24 if ("sssp24" in what or "ds24" in what) else 22
+    n, s, d, v = capi.rmat_edges(sc, 16, seed=1, weight_max=127, weight_seed=2)
     src0 = int(s.min())
-    if "sssp22" in what:
+    if "sssp22" in what or "sssp24" in what:
         G = capi.Graph.from_edges(n, s, d, v, capi.SSSP_DTYPE, threads=4, build_mask=2)
         for rep in range(2):
             inf = np.zeros(1, capi.SSSP_DTYPE)
@@ -48,16 +49,19 @@ if "sssp22" in what or "ds22" in what:
             G.set_vertexproperty(src0, np.zeros(1, capi.SSSP_DTYPE)[0])
             G.set_active(src0)
             st = G.run(capi.PROG_SSSP, None, -1)
-        print("SSSP RMAT-22: %d iterations %.3f ms -> %.1f GTEPS" % (st.iterations, st.ms_total, len(s) / st.ms_total / 1e6))
+        print("SSSP RMAT-%d: %d iterations %.3f ms -> %.1f GTEPS, push passes %d, entries swept %d" % (
+            sc, st.iterations, st.ms_total, len(s) / st.ms_total / 1e6, st.push_passes, st.edges_processed))
         G.close()
-    if "ds22" in what:
+    if "ds22" in what or "ds24" in what:
         t0 = time.time()
         dist, bucket, nb, reach = apps.deltastepping(n, s, d, v, 16, src0, threads=4)
-        print("DeltaStepping RMAT-22 delta 16: %d buckets, %d reachable, %.1f ms wall incl. build" % (nb, reach, (time.time() - t0) * 1e3))
+        print("DeltaStepping RMAT-%d delta 16: %d buckets, %d reachable, %.1f ms wall incl. build" % (sc, nb, reach, (time.time() - t0) * 1e3))
 
-if "sgd" in what:
+if "sgd" in what or "sgdbig" in what:
     rng = np.random.default_rng(3)
     nu, ni, nnz, K = 1000000, 100000, 20000000, 32
+    if "sgdbig" in what:  # BASELINE.json config 4 shape (10 M x 1 M); nnz is a parameter there
+        nu, ni, nnz = 10000000, 1000000, 200000000
     u = rng.integers(1, nu + 1, nnz).astype(np.int32)
     it = (np.floor(np.exp(rng.random(nnz) * np.log(ni))).astype(np.int64).clip(1, ni) + nu).astype(np.int32)
     r = rng.integers(1, 6, nnz).astype(np.int32)

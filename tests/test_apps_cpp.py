@@ -92,3 +92,10 @@ def test_sgd_app_on_ratings7(tmp_path):
     assert abs(rm[0] - float(g["rmse0"])) < 1e-5 and abs(rm[1] - float(g["rmse1"])) < 1e-5
     a = np.loadtxt(d)
     assert np.max(np.abs(a[:, 1:] - g["lv"]) / np.abs(g["lv"])) <= 1e-6
+
+
+@pytest.mark.parametrize("n", [5, 500])
+def test_apply_edges_cpp(n):
+    """test/test_apply_edges.cpp of the reference (applyToAllEdges + getEdgelist) on the C++ mirror, and SSSP over
+    the rewritten weights (the device matrices carry them)"""
+    assert "apply_edges ok" in run("ApplyEdgesCheck", n)
