@@ -97,7 +97,7 @@ SYMBOLS = [
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
     "gm_debug_fold_f32_device", "gm_graph_push_ready", "gm_graph_set_push_policy", "gm_push_count", "gm_push_prepare",
-    "gm_push_sort", "gm_graph_set_edge_values",
+    "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts",
 ]
 
 

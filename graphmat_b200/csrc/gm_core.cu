@@ -1210,15 +1210,17 @@ extern "C" int gm_graph_set_exchange(gm_graph* g, gm_allgather_fn allgather, gm_
   g->xctx = ctx;
   return 0;
 }
-extern "C" int gm_graph_exchange_x(gm_graph* g, gm_vectors* v) {
+extern "C" int gm_graph_exchange_x_parts(gm_graph* g, gm_vectors* v, int values, int bits) {
   if (g->world == 1) return 0;
   if (!g->allgather) {
     gm_set_error("world > 1 but no exchange functions were registered (gm_graph_set_exchange)");
     return 1;
   }
-  if (g->allgather(g->xctx, v->x_val, (long long)g->n_pad * v->sizeof_T, (void*)g->stream)) return 1;
-  return g->allgather(g->xctx, v->x_bits, (long long)(g->n_pad >> 5) * 4, (void*)g->stream);
+  if (values && g->allgather(g->xctx, v->x_val, (long long)g->n_pad * v->sizeof_T, (void*)g->stream)) return 1;
+  if (bits && g->allgather(g->xctx, v->x_bits, (long long)(g->n_pad >> 5) * 4, (void*)g->stream)) return 1;
+  return 0;
 }
+extern "C" int gm_graph_exchange_x(gm_graph* g, gm_vectors* v) { return gm_graph_exchange_x_parts(g, v, 1, 1); }
 extern "C" int gm_graph_allreduce_or(gm_graph* g, int* flag) {
   if (g->world == 1) return 0;
   if (!g->allreduce_or) {

@@ -1366,7 +1366,8 @@ struct engine {
     while (1) {
       GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
       if (!(fuse && it > 0) && send(prog, gv, vv, &sc)) return 1;  // fused: the previous apply already sent
-      if (gv.world > 1 && gm_graph_exchange_x(g, tmp)) return 1;
+      // fused ALL_VERTICES programs re-arm every x bit in every iteration: the bit words are exchanged once
+      if (gv.world > 1 && gm_graph_exchange_x_parts(g, tmp, 1, (fuse && it > 0) ? 0 : 1)) return 1;
       cudaEvent_t es0 = s0, es1 = s1;
       if (async && timing) {
         es0 = evs[2 * pending];

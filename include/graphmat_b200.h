@@ -160,6 +160,8 @@ typedef int (*gm_allgather_fn)(void* ctx, void* buf, long long bytes_per_rank, v
 typedef int (*gm_allreduce_or_fn)(void* ctx, int* host_flag);
 int gm_graph_set_exchange(gm_graph* g, gm_allgather_fn allgather, gm_allreduce_or_fn allreduce_or, void* ctx);
 int gm_graph_exchange_x(gm_graph* g, gm_vectors* v);     /* all-gather x values + bit words in place */
+int gm_graph_exchange_x_parts(gm_graph* g, gm_vectors* v, int values, int bits); /* ... either half alone: an
+                                                            ALL_VERTICES program's bit words never change after iteration 0 */
 int gm_graph_allreduce_or(gm_graph* g, int* flag);       /* "some vertex changed" across ranks */
 
 /* ---- sparse frontiers: push SpMSpV over the active columns only.  The reference's my_spmspv visits only
