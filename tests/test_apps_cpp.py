@@ -24,11 +24,12 @@ def write_mtx(prefix, m, n, src, dst, val):
         f.write(rec.tobytes())
 
 
-def run(app, *args, threads=4):
+def run(app, *args, threads=4, extra_env=None):
     exe = os.path.join(BIN, app)
     if not os.path.exists(exe):
         pytest.fail("apps/bin/%s is not built (python -c 'import __graft_entry__ as g; g.build()')" % app)
     env = dict(os.environ, GM_REF_THREADS=str(threads))
+    env.update(extra_env or {})
     out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     return out.stdout
@@ -99,3 +100,13 @@ def test_apply_edges_cpp(n):
     """test/test_apply_edges.cpp of the reference (applyToAllEdges + getEdgelist) on the C++ mirror, and SSSP over
     the rewritten weights (the device matrices carry them)"""
     assert "apply_edges ok" in run("ApplyEdgesCheck", n)
+
+
+@pytest.mark.parametrize("policy", ["default", "always_push", "never_push"])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_custom_program_cpp(policy, threads):
+    """a user-defined, trait-less, order-sensitive (fp32 sum) ACTIVE_ONLY program through the C++ surface equals
+    the reference's definition evaluated on the host, bit for bit, on the row-major and on the push path"""
+    env = {"default": {}, "always_push": {"GM_PUSH_DIVISOR": "1", "GM_PUSH_MIN_NNZ": "0"},
+           "never_push": {"GM_PUSH_DIVISOR": "0"}}[policy]
+    assert "custom program ok" in run("CustomProgramCheck", 6, threads=threads, extra_env=env)

@@ -120,8 +120,9 @@ def test_two_rank_pagerank_gloo():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("push", [False, True])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_engine_one_gpu(world):
+def test_sharded_engine_one_gpu(world, push):
     from graphmat_b200 import capi, exchange
     n, s, d, v = util.rmat_numpy(12, weight_max=127)
     src0 = util.first_source(s)
@@ -154,6 +155,8 @@ def test_sharded_engine_one_gpu(world):
     # ---- BFS ----
     graphs = [capi.Graph.from_edges(n, s, d, None, capi.BFS_DTYPE, threads=threads, rank=r, world=world,
                                     heavy_threshold=64, coop_threshold=512) for r in range(world)]
+    for g in graphs:
+        g.set_push_policy(1, 0) if push else g.set_push_policy(0, 0)   # every pass / no pass on the sparse-frontier path
     vecs = [capi.Vectors(g, capi.PROG_BFS) for g in graphs]
     lr = exchange.LocalRanks(graphs, vecs)
     vp = np.zeros(n, capi.BFS_DTYPE)
