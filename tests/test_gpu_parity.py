@@ -178,19 +178,25 @@ def test_empty_and_edge_cases():
     assert allv["distance"][49] == 350 and allv["distance"][0] == 7
 
 
-def test_properties_at_scale():
-    """RMAT-20 (16.8 M edges): size-independent checks instead of the oracle."""
-    Gd = capi.Graph.rmat(20, capi.PR_DTYPE, seed=1, threads=4)
+@pytest.mark.parametrize("scale", [20, 22])
+def test_properties_at_scale(scale):
+    """RMAT-20 (16.8 M edges) and RMAT-22 (67 M edges, BASELINE.json's BFS configuration): size-independent checks
+    instead of the oracle -- Degree == out-degree histogram, PageRank only moves vertices that received a message,
+    Graph500-style BFS validation (tree edges exist, levels differ by one, no edge skips a level), SSSP distances
+    satisfy every edge's triangle inequality and are attained by some in-edge."""
+    Gd = capi.Graph.rmat(scale, capi.PR_DTYPE, seed=1, threads=4)
     n = Gd.nvertices
     pr, deg, it = apps.pagerank(n, None, None, graph=Gd, iterations=3)
-    _, s, d, _ = capi.rmat_edges(20, 16, seed=1)
+    Gd.close()
+    _, s, d, w = capi.rmat_edges(scale, 16, seed=1, weight_max=127)
     assert (deg == np.bincount(s - 1, minlength=n)).all()          # Degree pass == out-degree histogram
     indeg = np.bincount(d - 1, minlength=n)
     assert (pr[indeg == 0] == np.float32(0.3)).all()                # apply only where a message arrived
     assert np.isfinite(pr).all() and (pr >= np.float32(0.3) - 1e-6).all()
     src0 = util.first_source(s)
-    Gb = capi.Graph.rmat(20, capi.BFS_DTYPE, seed=1, threads=4)
+    Gb = capi.Graph.rmat(scale, capi.BFS_DTYPE, seed=1, threads=4, build_mask=2)
     depth, parent, bit, reach = apps.bfs(n, None, None, src0, graph=Gb)
+    Gb.close()
     vis = depth < 0xFFFFFFFF
     assert reach == vis.sum() and depth[src0 - 1] == 0
     # every visited non-source vertex has a visited parent exactly one level up, and (parent, v) is an edge
@@ -198,7 +204,6 @@ def test_properties_at_scale():
     idx = idx[idx != src0 - 1]
     p = parent[idx].astype(np.int64)
     assert (depth[p - 1] + 1 == depth[idx]).all()
-    edges = set(zip(s.tolist(), d.tolist())) if n <= (1 << 16) else None
     key = s.astype(np.int64) * (n + 1) + d
     key.sort()
     q = p * (n + 1) + (idx + 1)
@@ -206,6 +211,21 @@ def test_properties_at_scale():
     assert (key[np.minimum(pos, len(key) - 1)] == q).all()
     # no edge skips a level
     assert (depth[d - 1][vis[s - 1]] <= depth[s - 1][vis[s - 1]] + 1).all()
+    del key
+    # SSSP: fixed point of the relaxation
+    Gs = capi.Graph.rmat(scale, capi.SSSP_DTYPE, seed=1, weight_max=127, threads=4, build_mask=2)
+    dist, sit, sreach = apps.sssp(n, None, None, None, src0, graph=Gs)
+    Gs.close()
+    dd = dist.astype(np.int64)
+    fin = dist < 0xFFFFFFFF
+    assert sreach == fin.sum() == reach and dist[src0 - 1] == 0
+    es = fin[s - 1]
+    assert (dd[d - 1][es] <= dd[s - 1][es] + w[es]).all()          # no edge can still relax
+    best = np.full(n, np.iinfo(np.int64).max)
+    np.minimum.at(best, d[es] - 1, dd[s[es] - 1] + w[es])
+    chk = fin.copy()
+    chk[src0 - 1] = False
+    assert (best[chk] == dd[chk]).all()                             # every distance is attained by an in-edge
 
 
 # ---- sparse-frontier (push) path: every SpMSpV pass forced through it must still equal the oracle ----
