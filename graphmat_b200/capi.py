@@ -49,7 +49,7 @@ class MatrixView(C.Structure):
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
                 ("nnz", C.c_longlong), ("n_segs", C.c_int), ("seg_len", C.c_int), ("seg_ptr", C.c_void_p),
                 ("seg_row", C.c_void_p), ("c_ptr", C.c_void_p), ("c_row", C.c_void_p), ("c_rank", C.c_void_p),
-                ("c_val", C.c_void_p), ("rank_bits", C.c_int)]
+                ("c_val", C.c_void_p), ("rank_bits", C.c_int), ("n_long", C.c_int), ("long_entries", C.c_longlong)]
 
 
 class GraphView(C.Structure):

@@ -364,6 +364,16 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   M.n_heavy = n_heavy;
   M.n_slices = n_slices;
   M.n_coop = std::min(hc[2], n_heavy);
+  {
+    int* cl = nullptr;
+    if (dalloc(&cl, 1)) return 1;
+    CK(cudaMemsetAsync(cl, 0, 4, st));
+    k_count_heavy<<<nblk(n_pad), 256, 0, st>>>(M.row_len, n_pad, std::max(g->long_threshold, g->coop_threshold), cl);
+    int nl = 0;
+    if (d2h(&nl, cl, 4, st)) return 1;
+    cudaFree(cl);
+    M.n_long = std::min(nl, M.n_coop);
+  }
   M.n_slices_wide = hc[3] > n_heavy ? std::min(n_slices, (hc[3] - n_heavy + 31) / 32) : 0;
   M.identity = identity ? 1 : 0;
 
@@ -383,6 +393,8 @@ static int build_matrix(gm_graph* g, gm_matrix& M, const int* rows, const int* c
   if (dalloc(&M.h_ptr, (size_t)n_heavy + 1)) return 1;
   CK(cudaMemcpyAsync(M.h_ptr, row_ptr, ((size_t)n_heavy + 1) * 8, cudaMemcpyDeviceToDevice, st));
   if (d2h(&nh, row_ptr + n_heavy, 8, st)) return 1;
+  M.long_entries = 0;
+  if (M.n_long > 0 && d2h(&M.long_entries, row_ptr + M.n_long, 8, st)) return 1;
   E* hv = nullptr;
   if (dalloc(&M.h_col, nh + 16) || dalloc(&hv, nh + 16)) return 1;  // +16: kernels read aligned groups of 8
   CK(cudaMemsetAsync(M.h_col + nh, 0, 16 * 4, st));
@@ -468,6 +480,8 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->c_rank = M.c_rank;
   v->c_val = M.c_val;
   v->rank_bits = M.rank_bits;
+  v->n_long = M.n_long;
+  v->long_entries = M.long_entries;
 }
 
 // d_src/d_dst: device copies owned by this call (public ids, overwritten with native ids)
@@ -565,6 +579,10 @@ static gm_graph* graph_new(int nvertices, int sizeof_E, int sizeof_V, const gm_g
   g->heavy_auto = !(opts && opts->heavy_threshold > 0);
   if (const char* e = getenv("GM_HEAVY_THRESHOLD")) if (g->heavy_auto) { g->heavy_threshold = atoi(e); g->heavy_auto = false; }
   if (const char* e = getenv("GM_COOP_THRESHOLD")) if (!(opts && opts->coop_threshold > 0)) g->coop_threshold = atoi(e);
+  // staging the longest rows pays when a rank's pass is short enough for one row to be its critical path
+  // (sharded runs); on one GPU the extra gather kernel only competes with the sliced-ELL rows (measured)
+  g->long_threshold = g->world > 1 ? GM_DEFAULT_LONG_THRESHOLD : 0x7fffffff;
+  if (const char* e = getenv("GM_LONG_ROW")) g->long_threshold = atoi(e);
   int per = (nvertices + g->world - 1) / g->world;
   g->n_pad = std::max(32, (per + 31) / 32 * 32);
   g->n_local = nvertices > g->rank ? (nvertices - g->rank + g->world - 1) / g->world : 0;

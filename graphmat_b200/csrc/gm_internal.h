@@ -11,6 +11,7 @@
 #define GM_DEFAULT_HEAVY_THRESHOLD 4096
 #define GM_DEFAULT_COOP_THRESHOLD 16384
 #define GM_SEG_LEN 2048
+#define GM_DEFAULT_LONG_THRESHOLD 32768
 
 void gm_set_error(const std::string& s);
 
@@ -36,6 +37,8 @@ struct gm_matrix {
   int* c_rank = nullptr;       // position of the entry in its row's fold order
   void* c_val = nullptr;       // edge value
   int rank_bits = 0;           // bits needed for c_rank
+  int n_long = 0;              // rows longer than gm_graph::long_threshold (a prefix: rows are stored longest first)
+  long long long_entries = 0;  // h_ptr[n_long]
   bool push_built = false;
 };
 
@@ -59,6 +62,7 @@ struct gm_graph {
   cudaStream_t stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int hot_limit = -1;
+  int long_threshold = GM_DEFAULT_LONG_THRESHOLD;
   void* push_scratch = nullptr;  // triples + sort buffers of the sparse-frontier path, grown geometrically
   size_t push_scratch_bytes = 0;
   int push_divisor = 16;

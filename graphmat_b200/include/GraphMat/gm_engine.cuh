@@ -737,11 +737,32 @@ __global__ void __launch_bounds__(128)
 // warp whose exit value would leave the binade (or that saw an addend the scan cannot
 // prove).  Warps before it are applied, that warp alone runs the warp-level fold from
 // its exact entry value, and the remaining warps are re-scanned under the new binade.
-template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W>
+// The few rows above gm_matrix_view::n_long entries are the critical path of a pass (one block walks the row
+// round by round, each round an index load, then a gather, then the scan): their gathers are hoisted out of
+// the block.  k_stage_rows lets the whole GPU write x[h_col[k]] for those rows into a dense staging array;
+// k_heavy_fadd32<..., STAGED> then folds from that array: one coalesced 32-byte load per lane and round, the
+// same addends in the same order.
+template <class T>
+__global__ void __launch_bounds__(256)
+    k_stage_rows(const int* __restrict__ h_col, long long n_entries, const T* __restrict__ x, int hot_limit,
+                 T* __restrict__ staged) {
+  const long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n_entries) return;
+  int c[8];
+  *reinterpret_cast<int4*>(&c[0]) = ld_stream4(h_col + i0);
+  *reinterpret_cast<int4*>(&c[4]) = ld_stream4(h_col + i0 + 4);
+  T v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = ld_gather(x, c[j], hot_limit);  // the pad behind the last row holds column 0
+#pragma unroll
+  for (int j = 0; j < 8; j++) staged[i0 + j] = v[j];
+}
+
+template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W, bool STAGED = false>
 __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit,
                    const T* __restrict__ x, const unsigned* __restrict__ xbits, float* __restrict__ y,
-                   unsigned* __restrict__ ybits) {
+                   unsigned* __restrict__ ybits, const T* __restrict__ staged = nullptr) {
   const P& prog = pb.get();
   constexpr int WPB = (W == 1) ? 4 : W;  // warps per block
   __shared__ float sm_s;
@@ -771,16 +792,27 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
       if (i0 < end && i0 + 8 > beg) {
         int c[8];
         E ev[8];
-        *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
-        *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
+        if constexpr (!STAGED) {
+          *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
+          *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) ev[j] = ld_stream(vals + i0 + j);
         T xv[8];
+        if constexpr (STAGED) {
+          static_assert(sizeof(T) == 4, "staged rows hold 4-byte messages");
+          *reinterpret_cast<int4*>(&xv[0]) = __ldg(reinterpret_cast<const int4*>(staged + i0));
+          *reinterpret_cast<int4*>(&xv[4]) = __ldg(reinterpret_cast<const int4*>(staged + i0 + 4));
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          bool on = (i0 + j >= beg) && (i0 + j < end);
-          if (on && !ALLACT) on = test_bit(xbits, c[j]);
-          if (on) { xv[j] = ld_gather(x, c[j], hot_limit); vmask |= 1u << j; }
+          for (int j = 0; j < 8; j++)
+            if ((i0 + j >= beg) && (i0 + j < end)) vmask |= 1u << j;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            bool on = (i0 + j >= beg) && (i0 + j < end);
+            if (on && !ALLACT) on = test_bit(xbits, c[j]);
+            if (on) { xv[j] = ld_gather(x, c[j], hot_limit); vmask |= 1u << j; }
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -1090,9 +1122,26 @@ struct engine {
     static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
     if constexpr (FADD) {
       const int n_coop = M.n_coop;
-      if (n_coop > 0 && !(dbg & 1)) {
-        int blocks = n_coop < 148 * 64 ? n_coop : 148 * 64;
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, 0, n_coop, hot, x, xbits, (float*)y, ybits);
+      int coop_begin = 0;
+      if constexpr (ALLACT && sizeof(T) == 4) {
+        // the longest rows: gathers by the whole GPU into a staging array, then one block per row folds from it
+        static const bool no_stage = getenv("GM_NO_STAGE") != nullptr;
+        if (M.n_long > 0 && !no_stage && !(dbg & 1)) {
+          void* scratch = nullptr;
+          if (gm_vectors_scratch(vecs, (M.long_entries + 64) * (long long)sizeof(T), &scratch)) return 1;
+          T* staged = (T*)scratch;
+          const long long groups = (M.long_entries + 7) / 8;
+          k_stage_rows<T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(M.h_col, M.long_entries, x, hot, staged);
+          // 32 warps per row: rounds of 8192 addends halve the number of serial rounds of the longest row
+          k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 32, true><<<M.n_long, 32 * 32, 0, st>>>(pb, M, 0, M.n_long, hot, x, xbits,
+                                                                                          (float*)y, ybits, staged);
+          if (sc) sc->launches += 2;
+          coop_begin = M.n_long;
+        }
+      }
+      if (n_coop > coop_begin && !(dbg & 1)) {
+        int blocks = n_coop - coop_begin < 148 * 64 ? n_coop - coop_begin : 148 * 64;
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, coop_begin, n_coop, hot, x, xbits, (float*)y, ybits);
         if (sc) sc->launches++;
       }
       if (M.n_heavy > n_coop && !(dbg & 2)) {

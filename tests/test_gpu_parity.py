@@ -331,3 +331,16 @@ def test_set_edge_values_refills_both_matrices():
     src1 = util.first_source(d)
     dist, st = _sssp_run(Gt, src1)
     assert (dist == port.sssp(n, d, s, v2, src1, threads=4)[0]).all()
+
+
+def test_staged_long_rows_pagerank(monkeypatch):
+    """the longest rows' gathers hoisted into a staging array (k_stage_rows + k_heavy_fadd32<STAGED>): same bits"""
+    n, s, d, _ = capi.rmat_edges(15, 16, seed=5)
+    monkeypatch.setenv("GM_LONG_ROW", "700")
+    Gd = capi.Graph.from_edges(n, s, d, None, capi.PR_DTYPE, threads=4, heavy_threshold=128, coop_threshold=300)
+    monkeypatch.delenv("GM_LONG_ROW")
+    v = Gd.view()
+    assert v.AT.n_long > 0 and v.AT.n_long < v.AT.n_coop and v.AT.long_entries > 700 * v.AT.n_long
+    a = apps.pagerank(n, None, None, graph=Gd, iterations=8)
+    b = port.pagerank(n, s, d, None, threads=4, iterations=8)
+    assert (a[1] == b[1]).all() and (a[0] == b[0]).all()
