@@ -67,6 +67,13 @@ class VectorsView(C.Structure):
                 ("y_val", C.c_void_p), ("y_bits", C.c_void_p)]
 
 
+class PushPlan(C.Structure):
+    _fields_ = [("n_active", C.c_int), ("n_entries", C.c_longlong), ("f_col", C.c_void_p), ("f_off", C.c_void_p),
+                ("keys", C.c_void_p), ("order", C.c_void_p), ("vals", C.c_void_p), ("keys_alt", C.c_void_p),
+                ("order_alt", C.c_void_p), ("sort_tmp", C.c_void_p), ("sort_tmp_bytes", C.c_longlong),
+                ("key_bits", C.c_int)]
+
+
 class PageRankState(C.Structure):
     _fields_ = [("alpha", C.c_float)]
 
@@ -97,7 +104,7 @@ SYMBOLS = [
     "gm_graph_set_exchange", "gm_graph_exchange_x", "gm_graph_allreduce_or", "gm_program_sizes", "gm_run_program",
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
     "gm_debug_fold_f32_device", "gm_graph_push_ready", "gm_graph_set_push_policy", "gm_push_count", "gm_push_prepare",
-    "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts",
+    "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts", "gm_abi_struct_sizes",
 ]
 
 

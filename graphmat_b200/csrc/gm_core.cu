@@ -27,6 +27,15 @@
 static thread_local std::string g_err;
 void gm_set_error(const std::string& s) { g_err = s; }
 extern "C" const char* gm_last_error(void) { return g_err.c_str(); }
+extern "C" int gm_abi_struct_sizes(int out[6]) {
+  out[0] = (int)sizeof(gm_graph_opts);
+  out[1] = (int)sizeof(gm_matrix_view);
+  out[2] = (int)sizeof(gm_graph_view);
+  out[3] = (int)sizeof(gm_vectors_view);
+  out[4] = (int)sizeof(gm_run_stats);
+  out[5] = (int)sizeof(gm_push_plan);
+  return 0;
+}
 
 #define CK(call)                                                                             \
   do {                                                                                       \

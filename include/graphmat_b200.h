@@ -113,6 +113,9 @@ typedef struct gm_run_stats {
 } gm_run_stats;
 
 const char* gm_last_error(void);
+/* sizeof of the structs above as this library was compiled, in the order gm_graph_opts, gm_matrix_view, gm_graph_view,
+ * gm_vectors_view, gm_run_stats, gm_push_plan: lets a foreign-language binding verify its mirror of the layouts */
+int gm_abi_struct_sizes(int out[6]);
 int gm_set_device(int device);
 int gm_device_count(void);
 

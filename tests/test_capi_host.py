@@ -22,6 +22,14 @@ def test_library_exports_every_declared_symbol(gmlib):
         assert hasattr(gmlib, name), name
 
 
+def test_binding_mirrors_the_struct_layouts(gmlib):
+    """capi.py's ctypes mirrors have the sizes the library was compiled with (a silent mismatch would shift fields)"""
+    out = (C.c_int * 6)()
+    assert gmlib.gm_abi_struct_sizes(out) == 0
+    mirrors = [capi.GraphOpts, capi.MatrixView, capi.GraphView, capi.VectorsView, capi.RunStats, capi.PushPlan]
+    assert list(out) == [C.sizeof(m) for m in mirrors]
+
+
 def test_struct_sizes_match_programs(gmlib):
     for prog, dt in [(capi.PROG_PAGERANK, capi.PR_DTYPE), (capi.PROG_DEGREE, capi.PR_DTYPE),
                      (capi.PROG_BFS, capi.BFS_DTYPE), (capi.PROG_SSSP, capi.SSSP_DTYPE),
