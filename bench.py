@@ -126,7 +126,7 @@ def run_reference(args):
         args.cpu_scale, nnz, args.iters, cores)
     line = {"impl": "reference", "metric": "GTEPS (PageRank, nnz*iterations/time of run_graph_program)", "value": gteps,
             "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "PageRank on synthetic RMAT scale-%d" % args.scale, "sample": sample},
             "cpu_baseline": {"value": gteps, "unit": "GTEPS", "cores": cores, "kind": "reference", "sample": sample},
