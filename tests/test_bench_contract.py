@@ -5,9 +5,16 @@ import os
 import subprocess
 import sys
 
+import pytest
+
+from oracle import ref
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ref.available("pagerank"),
+                               reason="oracle/_ref is built where /root/reference exists (make -C oracle ref)")
 
 
+@needs_ref
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-scale", "12",
                           "--steps", "1", "--warmup", "1", "--iters", "3"], capture_output=True, text=True, timeout=300)
