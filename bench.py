@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- GTEPS of the hot path (send -> SpMSpV -> apply) on synthetic RMAT.
+"""bench.py -- GTEPS of the hot path (send -> SpMSpV -> apply) on synthetic inputs.
 
-Workload (BASELINE.json metric / configs[2], north_star target): PageRank on RMAT scale-26
+Default workload (BASELINE.json metric / configs[2], north_star target): PageRank on RMAT scale-26
 (a,b,c = .57,.19,.19, edge factor 16, seed 1, duplicates kept), generated on the device.
 One "step" = run_graph_program(PageRank, ITERS iterations) over the resident graph.
 
-  value    whole-job GTEPS = nnz * ITERS * steps / device time, inputs resident in HBM
-  e2e      the same through the C ABI with HOST buffers: vertex properties uploaded from pinned
-           memory (setVertexproperty for all), run, results downloaded (getVertexproperty for all)
-  roofline dominant kernels = the SpMSpV pass (k_heavy + k_sell): algorithmic bytes
-           nnz*(sizeof(E)+4) + |active|*sizeof(M) per pass  /  CUDA-event time of the pass
-  cpu_baseline  the UNMODIFIED reference (oracle/_ref) on this box's host cores, bounded sample
+  value    whole-job GTEPS = nnz * ITERS * steps / device time (max over ranks), inputs resident in HBM
+  e2e      the same through the C ABI with HOST buffers: vertex properties uploaded from pinned memory
+           (setVertexproperty for all), run, results downloaded (getVertexproperty for all).  N > 1: every
+           rank moves only its 1/N slice of the public-order array over PCIe; the redistribution runs over
+           peer memory (gm_graph_{set,get}_vertexproperties_slice)
+  roofline dominant kernels = the SpMSpV pass: algorithmic bytes nnz*(sizeof(E)+4) + |active|*sizeof(M) per
+           pass / CUDA-event time of the pass; `achieved_dram` = DRAM bytes of the committed ncu capture / the
+           same time (PageRank never reads its edge values: the formula counts nnz*sizeof(E) bytes that do not move)
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) on this box's host cores, on a bounded sample
+  parity   the GPU engine on that same sample, compared bit for bit with the reference's output
 
+Other workloads (BASELINE configs 2, 4, 5): --workload bfs | sssp | deltastepping | sgd.
 `--impl reference` times only the reference CPU path (rank 0) and prints the same JSON shape.
-N > 1: one process per GPU (torchrun); rows are sharded one tile-row per rank, the message vector
-is all-gathered over NCCL every iteration.
+N > 1: one process per GPU (torchrun); rows are sharded one tile-row per rank; the message vector moves by
+stores into peer memory over NVLink from inside the kernels (CUDA IPC), NCCL all-gather as the fallback.
 """
 import argparse
 import ctypes as C
@@ -30,6 +35,12 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+METRIC = {"pagerank": "GTEPS (PageRank, nnz*iterations/time of run_graph_program)",
+          "bfs": "GTEPS (BFS, nnz/time of run_graph_program)",
+          "sssp": "GTEPS (SSSP, nnz/time of run_graph_program)",
+          "deltastepping": "GTEPS (DeltaStepping, nnz/time of the bucket loop)",
+          "sgd": "GTEPS (SGD, 2*nnz*iterations/time of run_graph_program)"}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -37,24 +48,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graphmat_b200", choices=["graphmat_b200", "reference"])
-    ap.add_argument("--scale", type=int, default=int(os.environ.get("GM_BENCH_SCALE", "26")))
-    ap.add_argument("--iters", type=int, default=10, help="PageRank iterations per step")
+    ap.add_argument("--workload", default="pagerank", choices=sorted(METRIC))
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("GM_BENCH_SCALE", "0")),
+                    help="RMAT scale (default: 26 pagerank, 22 bfs, 24 sssp/deltastepping)")
+    ap.add_argument("--iters", type=int, default=10, help="PageRank / SGD iterations per step")
     ap.add_argument("--threads", type=int, default=4, help="ref_threads of the logical layout")
-    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("GM_BENCH_CPU_SCALE", "22")))
+    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("GM_BENCH_CPU_SCALE", "0")),
+                    help="RMAT scale of the CPU sample; 0 = the largest the time budget allows")
+    ap.add_argument("--cpu-budget-s", type=float, default=0.0, help="time budget of the CPU sample (0 = default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bfs", action="store_true")
+    ap.add_argument("--bfs-scales", default="22,26")
     ap.add_argument("--heavy", type=int, default=0)
-    return ap.parse_args()
+    ap.add_argument("--ratings", type=int, default=500_000_000, help="sgd: number of ratings")
+    ap.add_argument("--no-peers", action="store_true", help="N > 1: NCCL all-gather callbacks instead of peer memory")
+    a = ap.parse_args()
+    if a.scale == 0:
+        a.scale = {"pagerank": 26, "bfs": 22, "sssp": 24, "deltastepping": 24, "sgd": 0}[a.workload]
+    return a
 
 
 def measured_traffic(scale, world):
     """DRAM bytes of one SpMSpV pass from the committed ncu --set full capture (profiles/), same workload only."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_pagerank_rmat26.json")))
-        if scale == 26 and world == 1:
-            return float(t["dram_bytes_per_pass"]), t["source"]
-    except Exception:
-        pass
+    for name in ("r2_traffic_pagerank_rmat26.json", "traffic_pagerank_rmat26.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if scale == 26 and world == 1:
+                return float(t["dram_bytes_per_pass"]), t["source"]
+        except Exception:
+            pass
     return None, None
 
 
@@ -98,94 +120,213 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_reference(scale, iters, steps, warmup):
-    """The unmodified reference on the host cores: PageRank, same generator, bounded scale."""
-    from graphmat_b200 import capi
+# ------------------------------------------------------------------------------------------------
+# The CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores.  Nothing of the product is
+# loaded here: the input comes from oracle/librmat.so (the same generator, restated).
+# ------------------------------------------------------------------------------------------------
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 32.0
+
+
+def cpu_env():
+    """thread placement of README.md:28-38 / BASELINE.md 3 -- must be set before libgomp starts"""
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("KMP_AFFINITY", "scatter")
+
+
+def pick_cpu_scale(target, budget_s, runs, iters, cores, forced=0):
+    """Largest RMAT scale <= target whose build + `runs` timed steps fit the budget (and host memory).
+    Measured on this box: a scale-20 probe, then x4.3 per two scales for the build (sort-dominated) and for
+    a step.  Returns (scale, reason)."""
     from oracle import ref
-    cores = os.cpu_count() or 1
-    n, s, d, _ = capi.rmat_edges(scale, 16, seed=1)
+    if forced:
+        return forced, "scale %d forced by --cpu-scale" % forced
+    probe = 20 if target > 20 else target
+    n, s, d, _ = ref.rmat_edges(probe, 16, seed=1)
+    t0 = time.time()
+    sess = ref.PageRankSession(n, s, d, None, threads=cores)
+    build = time.time() - t0
+    sess.run(iters)
+    _, ms = sess.run(iters)
+    sess.close()
+    mem = _mem_available_gb()
+    pick, est = probe, build + runs * ms * 1e-3
+    for sc in range(probe + 1, target + 1):
+        f = 2.08 ** (sc - probe)
+        e = build * f + runs * ms * 1e-3 * f
+        need_gb = (16 << sc) * 120 / 1e9  # edge list + both DCSC matrices + ingest copies: ~120 B per edge
+        if e > budget_s or need_gb > 0.6 * mem:
+            break
+        pick, est = sc, e
+    why = ("largest scale whose build + %d steps fit %.0f s on %d cores (scale-%d probe: build %.1f s, step %.0f ms; "
+           "estimate %.0f s; host memory %.0f GB free)" % (runs, budget_s, cores, probe, build, ms, est, mem))
+    if pick == target:
+        why = "full scale"
+    return pick, why
+
+
+def cpu_reference(scale, iters, steps, warmup, cores, keep=False):
+    """-> dict(gteps, ms_per_step, nnz, [pagerank, degree, edges])"""
+    from oracle import ref
+    n, s, d, _ = ref.rmat_edges(scale, 16, seed=1)
     sess = ref.PageRankSession(n, s, d, None, threads=cores)
     times = []
     for k in range(warmup + steps):
-        it, ms = sess.run(iters)
+        _, ms = sess.run(iters)
         if k >= warmup:
             times.append(ms)
+    out = {"nnz": len(s), "ms_per_step": sum(times) / len(times),
+           "gteps": len(s) * iters * len(times) / (sum(times) * 1e-3) / 1e9, "flavour": ref.build_flavour()[0]}
+    if keep:
+        out["pagerank"], out["degree"] = sess.get()
+        out["edges"] = (n, s, d)
     sess.close()
-    nnz = len(s)
-    total_ms = sum(times)
-    gteps = nnz * iters * len(times) / (total_ms * 1e-3) / 1e9
-    return gteps, total_ms / len(times), cores, nnz
+    return out
+
+
+def cpu_reference_other(workload, scale, cores, ratings):
+    """one run of the reference app on a bounded sample -> (gteps, ms, nnz, description)"""
+    from oracle import ref
+    if workload == "sgd":
+        m, nitems = 100_000, 10_000
+        u, it, r = synth_ratings(m, nitems, ratings)
+        _, _, _, ms = ref.sgd(m, m + nitems, u, it, r, K=32, iterations=2, threads=cores)
+        return 2 * len(u) * 2 / (ms * 1e-3) / 1e9, ms, len(u), "SGD K=32, %d x %d, %d ratings, 2 iterations" % (m, nitems, len(u))
+    n, s, d, v = ref.rmat_edges(scale, 16, seed=1, weight_max=0 if workload == "bfs" else 127, weight_seed=2)
+    src0 = int(s.min())
+    if workload == "bfs":
+        ms = ref.bfs(n, s, d, src0, None, threads=cores)[4]
+    elif workload == "sssp":
+        ms = ref.sssp(n, s, d, v, src0, threads=cores)[3]
+    else:
+        ms = ref.deltastepping(n, s, d, v, 16, src0, threads=cores)[4]
+    return len(s) / (ms * 1e-3) / 1e9, ms, len(s), "%s RMAT scale-%d (%d edges)" % (workload, scale, len(s))
+
+
+def synth_ratings(m, nitems, nnz, seed=3):
+    """user uniform, item Zipf(1.0), rating uniform 1..5; item ids offset by m (as in ratings7)"""
+    rng = np.random.default_rng(seed)
+    u = rng.integers(1, m + 1, nnz, dtype=np.int64).astype(np.int32)
+    w = 1.0 / np.arange(1, nitems + 1)
+    cdf = np.cumsum(w / w.sum())
+    it = (np.searchsorted(cdf, rng.random(nnz)) + 1 + m).astype(np.int32)
+    r = rng.integers(1, 6, nnz, dtype=np.int64).astype(np.int32)
+    return u, it, r
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    gteps, ms, cores, nnz = cpu_reference(args.cpu_scale, args.iters, args.steps, min(args.warmup, 1))
-    sample = "PageRank RMAT scale-%d (%d edges), %d iterations per step, 1 rank (stub MPI) x %d OpenMP threads" % (
-        args.cpu_scale, nnz, args.iters, cores)
-    line = {"impl": "reference", "metric": "GTEPS (PageRank, nnz*iterations/time of run_graph_program)", "value": gteps,
-            "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "PageRank on synthetic RMAT scale-%d" % args.scale, "sample": sample},
+    cpu_env()
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    budget = args.cpu_budget_s or 150.0
+    warm = args.warmup
+    if args.workload == "pagerank":
+        scale, why = pick_cpu_scale(args.scale, budget, warm + args.steps, args.iters, cores, args.cpu_scale)
+        r = cpu_reference(scale, args.iters, args.steps, warm, cores)
+        gteps, ms, nnz = r["gteps"], r["ms_per_step"], r["nnz"]
+        sample = ("PageRank RMAT scale-%d (%d edges), %d iterations per step, unmodified reference (%s build), 1 rank "
+                  "(stub MPI) x %d OpenMP threads, OMP_PROC_BIND=%s; %s" % (scale, nnz, args.iters, r["flavour"], cores,
+                                                                          os.environ.get("OMP_PROC_BIND"), why))
+        config = {"workload": "PageRank on synthetic RMAT scale-%d" % args.scale, "sample_scale": scale,
+                  "sample": sample, "iterations_per_step": args.iters, "edge_factor": 16, "rmat": "a,b,c=.57,.19,.19 seed=1"}
+    else:
+        scale = args.cpu_scale or min(args.scale, 20)
+        gteps, ms, nnz, what = cpu_reference_other(args.workload, scale, cores, min(args.ratings, 2_000_000))
+        sample = "%s, unmodified reference, 1 rank (stub MPI) x %d OpenMP threads, one run" % (what, cores)
+        config = {"workload": workload_name(args), "sample": sample}
+    line = {"impl": "reference", "metric": METRIC[args.workload], "value": gteps,
+            "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.workload == "sgd" else ("f32" if args.workload == "pagerank" else "u32"),
+            "data": "synthetic", "config": config,
             "cpu_baseline": {"value": gteps, "unit": "GTEPS", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": gteps, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:  # which of the repo's shared objects this process mapped: the checker's only, never the product's
+        libs = sorted({l.split()[-1][len(ROOT) + 1:] for l in open("/proc/self/maps") if ROOT in l and ".so" in l})
+        line["repo_libs_loaded"] = libs
+    except Exception:
+        pass
     print(json.dumps(line))
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+def workload_name(args):
+    if args.workload == "pagerank":
+        return "PageRank on synthetic RMAT scale-%d" % args.scale
+    if args.workload == "sgd":
+        return "SGD collaborative filtering on synthetic 10M x 1M ratings, K=32"
+    return "%s on synthetic %sRMAT scale-%d" % ({"bfs": "BFS", "sssp": "SSSP", "deltastepping": "DeltaStepping"}[args.workload],
+                                                "" if args.workload == "bfs" else "weighted ", args.scale)
 
+
+# ------------------------------------------------------------------------------------------------
+# The GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def setup(args):
     import torch
     from graphmat_b200 import capi
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    capi._check(capi.lib().gm_set_device(C.c_int(local)), "gm_set_device")
-    dist = None
-    if world > 1:
+    c = Ctx()
+    c.torch, c.capi = torch, capi
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(c.local)
+    capi._check(capi.lib().gm_set_device(C.c_int(c.local)), "gm_set_device")
+    c.dist = None
+    if c.world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
+        c.dist = dist
+    return c
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    t_build = time.time()
-    G = capi.Graph.rmat(args.scale, capi.PR_DTYPE, seed=1, threads=args.threads, rank=rank, world=world,
-                        heavy_threshold=args.heavy)
-    gv = G.view()
-    n, nnz = gv.nvertices, gv.nnz
-    tmp = capi.Vectors(G, capi.PROG_PAGERANK)
-    if world > 1:
-        from graphmat_b200 import exchange
-        exchange.attach(G, tmp, dist)
-    build_s = time.time() - t_build
+def barrier(c):
+    c.torch.cuda.synchronize()
+    if c.dist is not None:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
 
-    init = np.zeros(1, capi.PR_DTYPE)
-    init["pagerank"], init["degree"] = 0.3, 0
-    G.set_all_vertexproperty(init[0])
-    G.set_all_active()
-    G.run(capi.PROG_DEGREE, None, 1)  # out-degrees (src/PageRank.cpp:133-139), outside the timed region
-    state = capi.PageRankState(0.3)
 
-    def step():
-        G.set_all_active()
-        return G.run(capi.PROG_PAGERANK, state, args.iters, tmp)
+def max_over_ranks(c, vals):
+    if c.dist is None:
+        return list(vals)
+    t = c.torch.tensor(list(vals), device="cuda", dtype=c.torch.float64)
+    c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return t.tolist()
 
+
+def attach_exchange(c, G, args):
+    """-> description of the exchange; peers first (must precede the creation of the Vectors)"""
+    if c.world == 1:
+        return "1 GPU"
+    from graphmat_b200 import exchange
+    if not args.no_peers and exchange.attach_peers(G, c.dist):
+        return "one tile-row per GPU; x by stores into peer memory over NVLink (CUDA IPC) + barrier kernel"
+    exchange.attach(G, None, c.dist)
+    return "one tile-row per GPU; x all-gather over NCCL (callback per iteration)"
+
+
+def timed_steps(c, args, step):
+    """W warm-up steps, K timed ones between barriers -> (device ms, spmv ms, wall ms, launches, clocks)"""
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(c.local)
+    if c.rank == 0:
         sampler.start()
-    barrier()
+    barrier(c)
     t0 = time.perf_counter()
     dev_ms = spmv_ms = 0.0
     launches = 0
@@ -194,113 +335,201 @@ def main():
         dev_ms += st.ms_total
         spmv_ms += st.ms_spmv
         launches += st.kernel_launches
-    barrier()
+    barrier(c)
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
-    # max over ranks of the device time
-    if dist is not None:
-        t = torch.tensor([dev_ms, spmv_ms, wall_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, spmv_ms, wall_ms = t.tolist()
+    dev_ms, spmv_ms, wall_ms = max_over_ranks(c, [dev_ms, spmv_ms, wall_ms])
+    return dev_ms, spmv_ms, wall_ms, launches, sampler.summary()
+
+
+def bench_bfs_block(c, args, scale):
+    """BFS on RMAT-`scale` (configs[1] at 22), reported beside the headline"""
+    capi = c.capi
+    Gb = capi.Graph.rmat(scale, capi.BFS_DTYPE, seed=1, threads=args.threads, build_mask=2)
+    Gb.push_ready(1)  # column-major companion of the sparse-frontier path: graph construction, not BFS time
+    src0 = Gb.first_source()
+    nb = Gb.nvertices
+    vp = np.zeros(nb, capi.BFS_DTYPE)
+    vp["depth"] = 0xFFFFFFFF
+    vp["parent"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    vp["id"] = np.arange(1, nb + 1, dtype=np.uint64)
+    vp["depth"][src0 - 1] = 0
+    tmpb = capi.Vectors(Gb, capi.PROG_BFS)
+    best = None
+    for _ in range(4):
+        Gb.set_vertexproperties(vp)
+        Gb.set_all_inactive()
+        Gb.set_active(src0)
+        stb = Gb.run(capi.PROG_BFS, capi.BFSState(1), capi.UNTIL_CONVERGENCE, tmpb)
+        if best is None or stb.ms_total < best.ms_total:
+            best = stb
+    reach = int(Gb.reduce(capi.REDUCE_REACHABLE))
+    peak, _ = peaks()
+    swept = int(best.edges_processed)
+    out = {"workload": "BFS RMAT scale-%d" % scale, "gteps": Gb.nnz / (best.ms_total * 1e-3) / 1e9, "ms": best.ms_total,
+           "iterations": best.iterations, "reachable": reach, "source": src0, "push_passes": int(best.push_passes),
+           "entries_swept": swept, "launches": int(best.kernel_launches),
+           "roofline": {"bound": "hbm", "unit": "GB/s", "ms_in_passes": best.ms_spmv,
+                        "algorithmic_bytes": swept * 8 + reach * 8,
+                        "achieved": (swept * 8 + reach * 8) / (best.ms_spmv * 1e-3) / 1e9 if best.ms_spmv > 0 else None,
+                        "peak": peak,
+                        "note": "bytes = entries swept * (sizeof(E)+4) + frontier vertices * sizeof(M); a BFS pass is a few "
+                                "launch-latency-bound kernels, not a stream"}}
+    if out["roofline"]["achieved"]:
+        out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+    tmpb.close()
+    Gb.close()
+    return out
+
+
+def bench_pagerank(c, args):
+    capi, torch = c.capi, c.torch
+    rank, world = c.rank, c.world
+    t_build = time.time()
+    G = capi.Graph.rmat(args.scale, capi.PR_DTYPE, seed=1, threads=args.threads, rank=rank, world=world,
+                        heavy_threshold=args.heavy)
+    gv = G.view()
+    n, nnz = gv.nvertices, gv.nnz
+    sharding = attach_exchange(c, G, args)
+    tmp = capi.Vectors(G, capi.PROG_PAGERANK)
+    dtmp = capi.Vectors(G, capi.PROG_DEGREE)
+    build_s = time.time() - t_build
+
+    init = np.zeros(1, capi.PR_DTYPE)
+    init["pagerank"], init["degree"] = 0.3, 0
+    G.set_all_vertexproperty(init[0])
+    G.set_all_active()
+    G.run(capi.PROG_DEGREE, None, 1, dtmp)  # out-degrees (src/PageRank.cpp:133-139), outside the timed region
+    state = capi.PageRankState(0.3)
+
+    def step():
+        G.set_all_active()
+        return G.run(capi.PROG_PAGERANK, state, args.iters, tmp)
+
+    dev_ms, spmv_ms, wall_ms, launches, clocks = timed_steps(c, args, step)
     passes = args.iters * args.steps
     gteps = nnz * passes / (dev_ms * 1e-3) / 1e9
 
     # ---- e2e: host buffers in pinned memory, copies inside the timed region ----
     vdt = capi.PR_DTYPE
-    host_in = torch.empty(n * vdt.itemsize, dtype=torch.uint8).pin_memory()
-    host_out = torch.empty(n * vdt.itemsize, dtype=torch.uint8).pin_memory()
-    vp0 = G.get_vertexproperties()
+    sliced = world > 1 and G.peers_enabled()
+    lo, hi = G.slice_range(rank) if sliced else (0, n)
+    host_in = torch.empty(max(1, (hi - lo)) * vdt.itemsize, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty(max(1, (hi - lo)) * vdt.itemsize, dtype=torch.uint8).pin_memory()
+    if sliced:
+        G.get_vertexproperties_slice_ptr(host_in.data_ptr())
+        vp0 = np.frombuffer(host_in.numpy(), dtype=vdt)[:hi - lo]
+    else:
+        vp0 = np.frombuffer(host_in.numpy(), dtype=vdt)[:n]
+        vp0[:] = G.get_vertexproperties()
     vp0["pagerank"] = 0.3
-    np.frombuffer(host_in.numpy(), dtype=vdt)[:] = vp0
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
-        G.set_vertexproperties_ptr(host_in.data_ptr())
+        if sliced:
+            G.set_vertexproperties_slice_ptr(host_in.data_ptr())
+        else:
+            G.set_vertexproperties_ptr(host_in.data_ptr())
         G.set_all_active()
         G.run(capi.PROG_PAGERANK, state, args.iters, tmp)
-        G.get_vertexproperties_ptr(host_out.data_ptr())
+        if sliced:
+            G.get_vertexproperties_slice_ptr(host_out.data_ptr())
+        else:
+            G.get_vertexproperties_ptr(host_out.data_ptr())
 
     e2e_step()
-    barrier()
+    barrier(c)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    barrier()
+    barrier(c)
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
+    e2e_ms, = max_over_ranks(c, [e2e_ms])
     e2e_gteps = nnz * args.iters * e2e_steps / (e2e_ms * 1e-3) / 1e9
-
-    # ---- BFS on RMAT-22 (configs[1]), reported beside the headline ----
-    bfs = None
-    if not args.no_bfs and world == 1:
-        from graphmat_b200 import apps
-        Gb = capi.Graph.rmat(22, capi.BFS_DTYPE, seed=1, threads=args.threads, build_mask=2)
-        Gb.push_ready(1)  # column-major companion of the sparse-frontier path: graph construction, not BFS time
-        src0 = Gb.first_source()
-        nb = Gb.nvertices
-        vp = np.zeros(nb, capi.BFS_DTYPE)
-        best = None
-        for _ in range(4):
-            vp["depth"] = 0xFFFFFFFF
-            vp["parent"] = np.uint64(0xFFFFFFFFFFFFFFFF)
-            vp["id"] = np.arange(1, nb + 1, dtype=np.uint64)
-            vp["depth"][src0 - 1] = 0
-            Gb.set_vertexproperties(vp)
-            Gb.set_all_inactive()
-            Gb.set_active(src0)
-            stb = Gb.run(capi.PROG_BFS, capi.BFSState(1), capi.UNTIL_CONVERGENCE)
-            best = stb.ms_total if best is None else min(best, stb.ms_total)
-        reach = int(Gb.reduce(capi.REDUCE_REACHABLE))
-        bfs = {"workload": "BFS RMAT scale-22", "gteps": Gb.nnz / (best * 1e-3) / 1e9, "ms": best,
-               "iterations": stb.iterations, "reachable": reach, "source": src0,
-               "push_passes": int(stb.push_passes), "entries_swept": int(stb.edges_processed)}
-        Gb.close()
-
-    if rank == 0:
-        peak, peak_src = peaks()
-        # algorithmic bytes per SpMSpV pass: nnz*(sizeof(E)+sizeof(idx)) + |active|*sizeof(M)
-        alg_bytes = nnz * (4 + 4) + n * 4
-        ms_per_pass = spmv_ms / passes
-        traffic, traffic_src = measured_traffic(args.scale, world)
-        achieved = alg_bytes / world / (ms_per_pass * 1e-3) / 1e9  # per GPU
-        line = {
-            "metric": "GTEPS (PageRank, nnz*iterations/time of run_graph_program)", "value": gteps, "unit": "GTEPS",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PageRank on synthetic RMAT scale-%d" % args.scale, "vertices": n, "edges": nnz,
-                       "iterations_per_step": args.iters, "edge_factor": 16, "rmat": "a,b,c=.57,.19,.19 seed=1",
-                       "ref_threads": args.threads, "sharding": "one tile-row per GPU, x all-gather" if world > 1 else "1 GPU",
-                       "l2": "inputs (%.1f GB index stream) larger than L2, no flush" % (nnz * 4 / 1e9),
-                       "build_seconds": round(build_s, 2)},
-            "wall_ms_per_step": wall_ms / args.steps,
-            "e2e": {"value": e2e_gteps, "unit": "GTEPS", "h2d_bytes_per_step": n * vdt.itemsize,
-                    "d2h_bytes_per_step": n * vdt.itemsize, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "SpMSpV pass (k_heavy + k_sell)", "ms_per_launch": ms_per_pass,
-                         "algorithmic_bytes": alg_bytes // world, "peak_source": peak_src,
-                         "spmv_share_of_step": spmv_ms / dev_ms},
-            "clocks": sampler.summary(),
-        }
-        if bfs:
-            line["bfs"] = bfs
-        if not args.no_cpu and world == 1:
-            try:
-                cg, cms, cores, cnnz = cpu_reference(args.cpu_scale, args.iters, 2, 1)
-                line["cpu_baseline"] = {"value": cg, "unit": "GTEPS", "cores": cores, "kind": "reference",
-                                        "sample": "PageRank RMAT scale-%d (%d edges), %d iterations, unmodified reference, "
-                                                  "1 rank (stub MPI) x %d OpenMP threads" % (args.cpu_scale, cnnz, args.iters, cores)}
-            except Exception as e:  # the reference .so is test infrastructure; report, do not hide
-                line["cpu_baseline"] = {"value": None, "unit": "GTEPS", "cores": os.cpu_count(), "kind": "reference",
-                                        "sample": "unavailable: %s" % e}
-        print(json.dumps(line))
+    # bytes over PCIe per step, summed over the ranks
+    moved = n * vdt.itemsize if (sliced or world == 1) else n * vdt.itemsize * world
     tmp.close()
+    dtmp.close()
     G.close()
-    if dist is not None:
-        dist.destroy_process_group()
+
+    bfs = []
+    if not args.no_bfs and world == 1:
+        for sc in [int(x) for x in args.bfs_scales.split(",") if x]:
+            bfs.append(bench_bfs_block(c, args, sc))
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    # algorithmic bytes per SpMSpV pass (SURVEY 8d): nnz*(sizeof(E)+sizeof(idx)) + |active|*sizeof(M)
+    alg_bytes = nnz * (4 + 4) + n * 4
+    ms_per_pass = spmv_ms / passes
+    traffic, traffic_src = measured_traffic(args.scale, world)
+    achieved = alg_bytes / world / (ms_per_pass * 1e-3) / 1e9  # per GPU
+    line = {
+        "metric": METRIC["pagerank"], "value": gteps, "unit": "GTEPS",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "vertices": n, "edges": nnz,
+                   "iterations_per_step": args.iters, "edge_factor": 16, "rmat": "a,b,c=.57,.19,.19 seed=1",
+                   "ref_threads": args.threads, "sharding": sharding,
+                   "l2": "inputs (%.1f GB index stream) larger than L2, no flush" % (nnz * 4 / 1e9),
+                   "build_seconds": round(build_s, 2)},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": e2e_gteps, "unit": "GTEPS", "h2d_bytes_per_step": moved, "d2h_bytes_per_step": moved,
+                "ms_per_step": e2e_ms / e2e_steps,
+                "path": "each rank moves its 1/N public-order slice; redistribution over peer memory" if sliced else
+                        "whole vertex-property array per rank"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "achieved_dram": (traffic / (ms_per_pass * 1e-3) / 1e9) if traffic else None,
+                     "kernel": "SpMSpV pass with fused apply+send (k_sell + k_heavy_fadd32)",
+                     "ms_per_launch": ms_per_pass, "algorithmic_bytes": alg_bytes // world, "peak_source": peak_src,
+                     "spmv_share_of_step": spmv_ms / dev_ms,
+                     "note": "the formula counts nnz*sizeof(E) = %.2f GB of edge values that PageRank's process_message "
+                             "never reads (dead loads, removed at compile time)" % (nnz * 4 / 1e9)},
+        "clocks": clocks,
+    }
+    if bfs:
+        line["bfs"] = bfs[0]
+        if len(bfs) > 1:
+            line["bfs_more"] = bfs[1:]
+    if not args.no_cpu and world == 1:
+        try:
+            cpu_env()
+            cores = os.cpu_count() or 1
+            scale, why = pick_cpu_scale(args.scale, args.cpu_budget_s or 45.0, 3, args.iters, cores, args.cpu_scale)
+            r = cpu_reference(scale, args.iters, 2, 1, cores, keep=True)
+            sample = ("PageRank RMAT scale-%d (%d edges), %d iterations, unmodified reference (%s build), 1 rank (stub MPI) x "
+                      "%d OpenMP threads; %s" % (scale, r["nnz"], args.iters, r["flavour"], cores, why))
+            line["cpu_baseline"] = {"value": r["gteps"], "unit": "GTEPS", "cores": cores, "kind": "reference", "sample": sample}
+            # parity on the very sample the reference just computed: same edges, same logical layout (ref_threads = cores)
+            from graphmat_b200 import apps
+            ns, ss, ds = r["edges"]
+            pr, deg, _ = apps.pagerank(ns, ss, ds, None, threads=cores, iterations=args.iters)
+            rel = np.abs(pr.astype(np.float64) - r["pagerank"]) / np.maximum(np.abs(r["pagerank"]), 1e-300)
+            line["parity"] = {"checked": "GPU PageRank x%d on RMAT scale-%d vs the unmodified reference's output, same edges, "
+                                         "ref_threads=%d" % (args.iters, scale, cores),
+                              "bit_identical": bool((pr == r["pagerank"]).all() and (deg == r["degree"]).all()),
+                              "max_rel_err": float(rel.max()), "tolerance": 1e-6}
+        except Exception as e:  # the reference .so is test infrastructure; report, do not hide
+            line["cpu_baseline"] = {"value": None, "unit": "GTEPS", "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": "unavailable: %s" % e}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    c = setup(args)
+    if args.workload == "pagerank":
+        bench_pagerank(c, args)
+    else:
+        import bench_workloads
+        bench_workloads.run(c, args, sys.modules[__name__])
+    if c.dist is not None:
+        c.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -62,9 +62,14 @@ class GraphView(C.Structure):
                 ("push_divisor", C.c_int), ("push_min_nnz", C.c_longlong)]
 
 
+MAX_WORLD = 16
+
+
 class VectorsView(C.Structure):
     _fields_ = [("sizeof_T", C.c_int), ("sizeof_U", C.c_int), ("x_val", C.c_void_p), ("x_bits", C.c_void_p),
-                ("y_val", C.c_void_p), ("y_bits", C.c_void_p)]
+                ("y_val", C.c_void_p), ("y_bits", C.c_void_p), ("x_alt", C.c_void_p), ("n_peers", C.c_int),
+                ("peer_x_val", C.c_void_p * (MAX_WORLD - 1)), ("peer_x_alt", C.c_void_p * (MAX_WORLD - 1)),
+                ("peer_x_bits", C.c_void_p * (MAX_WORLD - 1))]
 
 
 class PushPlan(C.Structure):
@@ -92,6 +97,7 @@ class SGDState(C.Structure):
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)
 ALLREDUCE_OR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int))
+ALLGATHER_HOST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int)
 
 # every symbol include/graphmat_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -105,6 +111,9 @@ SYMBOLS = [
     "gm_step_send", "gm_step_spmspv", "gm_step_apply", "gm_graph_reduce", "gm_debug_fold_f32_host",
     "gm_debug_fold_f32_device", "gm_graph_push_ready", "gm_graph_set_push_policy", "gm_push_count", "gm_push_prepare",
     "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts", "gm_abi_struct_sizes",
+    "gm_graph_exchange_buffer", "gm_graph_enable_peers", "gm_graph_peers_enabled", "gm_graph_peer_barrier",
+    "gm_graph_push_x", "gm_vectors_need_alt", "gm_graph_slice_begin", "gm_graph_set_vertexproperties_slice",
+    "gm_graph_get_vertexproperties_slice",
 ]
 
 
@@ -291,6 +300,36 @@ class Graph:
     def set_exchange(self, allgather, allreduce_or):
         self._keep += [allgather, allreduce_or]
         _check(lib().gm_graph_set_exchange(self.h, allgather, allreduce_or, None), "gm_graph_set_exchange")
+
+    def enable_peers(self, allgather_host):
+        """Map the other ranks' buffers (collective).  Returns False when the devices cannot reach each other."""
+        self._keep.append(allgather_host)
+        rc = lib().gm_graph_enable_peers(self.h, allgather_host, None)
+        return rc == 0
+
+    def peers_enabled(self):
+        return bool(lib().gm_graph_peers_enabled(self.h))
+
+    def slice_range(self, rank):
+        f = lib().gm_graph_slice_begin
+        f.restype = C.c_longlong
+        return int(f(self.h, C.c_int(rank))), int(f(self.h, C.c_int(rank + 1)))
+
+    def set_vertexproperties_slice_ptr(self, ptr):
+        _check(lib().gm_graph_set_vertexproperties_slice(self.h, C.c_void_p(ptr)), "gm_graph_set_vertexproperties_slice")
+
+    def get_vertexproperties_slice_ptr(self, ptr):
+        _check(lib().gm_graph_get_vertexproperties_slice(self.h, C.c_void_p(ptr)), "gm_graph_get_vertexproperties_slice")
+
+    def set_vertexproperties_slice(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.vdtype)
+        self.set_vertexproperties_slice_ptr(arr.ctypes.data)
+
+    def get_vertexproperties_slice(self, rank):
+        lo, hi = self.slice_range(rank)
+        out = np.zeros(hi - lo, self.vdtype)
+        self.get_vertexproperties_slice_ptr(out.ctypes.data)
+        return out
 
     def synchronize(self):
         _check(lib().gm_graph_synchronize(self.h), "gm_graph_synchronize")

@@ -73,6 +73,14 @@ __global__ void k_to_native(int* ids, long long nnz, int n, int npart) {
   if (e < nnz) ids[e] = to_native0(ids[e], n, npart);
 }
 
+// public ids must lie in [1, n] (edgelist.h trusts the file header; a bad id would index out of bounds below)
+__global__ void k_check_ids(const int* a, const int* b, long long nnz, int n, int* bad) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  bool x = e < nnz && (a[e] < 1 || a[e] > n || b[e] < 1 || b[e] > n);
+  if (__ballot_sync(0xffffffffu, x) && (threadIdx.x & 31) == 0) atomicExch(bad, 1);
+}
+static int check_ids(const int* d_src, const int* d_dst, long long nnz, int n, cudaStream_t st, const char* who);
+
 __global__ void k_hist(const int* ids, long long nnz, int* cnt) {
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e < nnz) atomicAdd(cnt + ids[e], 1);
@@ -299,6 +307,23 @@ static int exclusive_scan_ll(const long long* in, long long* out, int n, cudaStr
   return 0;
 }
 
+static int check_ids(const int* d_src, const int* d_dst, long long nnz, int n, cudaStream_t st, const char* who) {
+  if (nnz == 0) return 0;
+  int* bad = nullptr;
+  if (dalloc(&bad, 1)) return 1;
+  CK(cudaMemsetAsync(bad, 0, 4, st));
+  k_check_ids<<<nblk(nnz), 256, 0, st>>>(d_src, d_dst, nnz, n, bad);
+  int h = 0;
+  int rc = d2h(&h, bad, 4, st);
+  cudaFree(bad);
+  if (rc) return 1;
+  if (h) {
+    gm_set_error(std::string(who) + ": an edge endpoint is outside [1, nvertices] (ids are public and 1-based)");
+    return 1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------- matrix build --
 static void matrix_free(gm_matrix& M) {
   cudaFree(M.c_ptr);
@@ -510,6 +535,7 @@ static int build_graph(gm_graph* g, int* d_src, int* d_dst, const E* d_val, long
   }
   // first public vertex with an out-edge (the benchmark's BFS/SSSP source)
   g->first_source = 0;
+  if (check_ids(d_src, d_dst, nnz, n, st, "gm_graph_create")) return 1;
   if (nnz) {
     int* dmin;
     if (dalloc(&dmin, 1)) return 1;
@@ -615,21 +641,26 @@ extern "C" int gm_graph_create(gm_graph** out, int nvertices, long long nnz, con
     return 1;
   }
   gm_graph* g = graph_new(nvertices, sizeof_E, sizeof_V, opts);
-  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    gm_set_error("gm_graph_create: cannot create a CUDA stream (no device?)");
+    delete g;
+    return 1;
+  }
   g->nnz = nnz;
   int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
-  if (dalloc(&d_src, nnz) || dalloc(&d_dst, nnz)) return 1;
   cudaMemcpyKind kind = (opts && opts->edges_on_device) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (nnz) {
-    CK(cudaMemcpyAsync(d_src, src, (size_t)nnz * 4, kind, g->stream));
-    CK(cudaMemcpyAsync(d_dst, dst, (size_t)nnz * 4, kind, g->stream));
-    if (val) {
-      if (dalloc(&d_val, nnz)) return 1;
-      CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, kind, g->stream));
+  int rc = dalloc(&d_src, nnz) || dalloc(&d_dst, nnz) || (val && dalloc(&d_val, nnz));
+  if (!rc && nnz) {
+    bool ok = cudaMemcpyAsync(d_src, src, (size_t)nnz * 4, kind, g->stream) == cudaSuccess &&
+              cudaMemcpyAsync(d_dst, dst, (size_t)nnz * 4, kind, g->stream) == cudaSuccess &&
+              (!val || cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, kind, g->stream) == cudaSuccess);
+    if (!ok) {
+      gm_set_error("gm_graph_create: copying the edge list to the device failed");
+      rc = 1;
     }
   }
   int mask = (opts && opts->build_mask) ? opts->build_mask : 3;
-  int rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
+  if (!rc) rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
   cudaFree(d_src);
   cudaFree(d_dst);
   cudaFree(d_val);
@@ -661,6 +692,10 @@ extern "C" int gm_graph_set_edge_values(gm_graph* g, long long nnz, const int* s
     CK(cudaMemcpyAsync(d_src, src, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_dst, dst, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    if (check_ids(d_src, d_dst, nnz, g->n, st, "gm_graph_set_edge_values")) {
+      cudaFree(d_src); cudaFree(d_dst); cudaFree(d_val);
+      return 1;
+    }
     const int npart = g->ref_threads * 16;
     k_to_native<<<nblk(nnz), 256, 0, st>>>(d_src, nnz, g->n, npart);
     k_to_native<<<nblk(nnz), 256, 0, st>>>(d_dst, nnz, g->n, npart);
@@ -691,15 +726,23 @@ extern "C" int gm_graph_create_rmat(gm_graph** out, int scale, int edge_factor, 
   }
   long long nnz = (long long)edge_factor << scale;
   gm_graph* g = graph_new(1 << scale, 4, sizeof_V, opts);
-  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    gm_set_error("gm_graph_create_rmat: cannot create a CUDA stream (no device?)");
+    delete g;
+    return 1;
+  }
   g->nnz = nnz;
   int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
-  if (dalloc(&d_src, nnz) || dalloc(&d_dst, nnz)) return 1;
-  if (weight_max > 0 && dalloc(&d_val, nnz)) return 1;
-  k_rmat<<<nblk(nnz), 256, 0, g->stream>>>(scale, seed, weight_max, weight_seed, nnz, d_src, d_dst, d_val);
-  CK(cudaGetLastError());
+  int rc = dalloc(&d_src, nnz) || dalloc(&d_dst, nnz) || (weight_max > 0 && dalloc(&d_val, nnz));
+  if (!rc) {
+    k_rmat<<<nblk(nnz), 256, 0, g->stream>>>(scale, seed, weight_max, weight_seed, nnz, d_src, d_dst, d_val);
+    if (cudaGetLastError() != cudaSuccess) {
+      gm_set_error("gm_graph_create_rmat: generator launch failed");
+      rc = 1;
+    }
+  }
   int mask = (opts && opts->build_mask) ? opts->build_mask : 3;
-  int rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
+  if (!rc) rc = build_graph<int>(g, d_src, d_dst, d_val, nnz, opts ? opts->order_like : nullptr, mask);
   cudaFree(d_src);
   cudaFree(d_dst);
   cudaFree(d_val);
@@ -723,6 +766,9 @@ extern "C" int gm_graph_destroy(gm_graph* g) {
   cudaFree(g->d_flags);
   if (g->h_flags) cudaFreeHost(g->h_flags);
   cudaFree(g->staging);
+  gm_sym_free(g, &g->sym_staging);
+  gm_sym_free(g, &g->sync);
+  for (void* p : g->retired) cudaFree(p);
   if (g->aux_stream) cudaStreamDestroy(g->aux_stream);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
@@ -1140,8 +1186,7 @@ extern "C" int gm_push_prepare(gm_graph* g, int which, gm_vectors* v, int n_acti
   const size_t b_key = up((size_t)n_entries * 8), b_ord = up((size_t)n_entries * 4), b_val = up((size_t)n_entries * v->sizeof_U);
   const size_t need = b_col + b_off + 2 * b_key + 2 * b_ord + b_val + tmp_b;
   if (need > g->push_scratch_bytes) {  // kept in the graph: run_graph_program may create its vectors per call
-    CK(cudaStreamSynchronize(st));
-    cudaFree(g->push_scratch);
+    if (g->push_scratch) g->retired.push_back(g->push_scratch);  // freed with the graph (cudaFree waits for the device)
     g->push_scratch = nullptr;
     g->push_scratch_bytes = 0;
     const size_t want = std::max(need + need / 2, (size_t)1 << 22);
@@ -1181,50 +1226,115 @@ extern "C" int gm_push_sort(gm_graph* g, gm_push_plan* plan) {
 
 // ------------------------------------------------------------------ vectors --
 extern "C" int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int sizeof_U) {
+  *out = nullptr;
+  if (sizeof_T <= 0 || sizeof_T % 4 || sizeof_U <= 0) {
+    gm_set_error("gm_vectors_create: sizeof_T must be a positive multiple of 4");
+    return 1;
+  }
   gm_vectors* v = new gm_vectors();
+  gm_graph* gm = const_cast<gm_graph*>(g);
+  v->g = gm;
   v->sizeof_T = sizeof_T;
   v->sizeof_U = sizeof_U;
   v->n_full = g->n_full;
   v->n_pad = g->n_pad;
-  CK(cudaMalloc(&v->x_val, (size_t)g->n_full * sizeof_T));
-  CK(cudaMalloc((void**)&v->x_bits, (size_t)(g->n_full >> 5) * 4));
-  CK(cudaMalloc(&v->y_val, (size_t)g->n_pad * sizeof_U));
-  CK(cudaMalloc((void**)&v->y_bits, (size_t)(g->n_pad >> 5) * 4));
-  CK(cudaMemsetAsync(v->x_val, 0, (size_t)g->n_full * sizeof_T, g->stream));
-  CK(cudaMemsetAsync(v->x_bits, 0, (size_t)(g->n_full >> 5) * 4, g->stream));
-  CK(cudaMemsetAsync(v->y_val, 0, (size_t)g->n_pad * sizeof_U, g->stream));
-  CK(cudaMemsetAsync(v->y_bits, 0, (size_t)(g->n_pad >> 5) * 4, g->stream));
-  CK(cudaStreamSynchronize(g->stream));
+  const size_t xb = (size_t)g->n_full * sizeof_T, bb = (size_t)(g->n_full >> 5) * 4;
+  if (g->peers_on) {  // the message buffers are mapped on every rank (gm_peer.cu); zero-filled by gm_sym_alloc
+    if (gm_sym_alloc(gm, xb, &v->s_val) || gm_sym_alloc(gm, bb, &v->s_bits)) {
+      gm_vectors_destroy(v);
+      return 1;
+    }
+    v->sym = true;
+    v->x_val = v->s_val.local;
+    v->x_bits = (unsigned*)v->s_bits.local;
+  } else {
+    if (cudaMalloc(&v->x_val, xb) != cudaSuccess || cudaMalloc((void**)&v->x_bits, bb) != cudaSuccess) {
+      gm_set_error("gm_vectors_create: out of device memory");
+      gm_vectors_destroy(v);
+      return 1;
+    }
+    cudaMemsetAsync(v->x_val, 0, xb, g->stream);
+    cudaMemsetAsync(v->x_bits, 0, bb, g->stream);
+  }
+  if (cudaMalloc(&v->y_val, (size_t)g->n_pad * sizeof_U) != cudaSuccess ||
+      cudaMalloc((void**)&v->y_bits, (size_t)(g->n_pad >> 5) * 4) != cudaSuccess) {
+    gm_set_error("gm_vectors_create: out of device memory");
+    gm_vectors_destroy(v);
+    return 1;
+  }
+  cudaMemsetAsync(v->y_val, 0, (size_t)g->n_pad * sizeof_U, g->stream);
+  cudaMemsetAsync(v->y_bits, 0, (size_t)(g->n_pad >> 5) * 4, g->stream);
+  if (cudaStreamSynchronize(g->stream) != cudaSuccess) {
+    gm_set_error("gm_vectors_create: device error");
+    gm_vectors_destroy(v);
+    return 1;
+  }
   *out = v;
+  return 0;
+}
+extern "C" int gm_vectors_need_alt(gm_vectors* v) {
+  if (v->x_alt) return 0;
+  const size_t xb = (size_t)v->n_full * v->sizeof_T;
+  if (v->sym) {
+    if (gm_sym_alloc(v->g, xb, &v->s_alt)) return 1;
+    v->x_alt = v->s_alt.local;
+  } else {
+    CK(cudaMalloc(&v->x_alt, xb));
+    CK(cudaMemsetAsync(v->x_alt, 0, xb, v->g->stream));
+  }
   return 0;
 }
 extern "C" int gm_vectors_destroy(gm_vectors* v) {
   if (!v) return 0;
-  cudaFree(v->x_val);
-  cudaFree(v->x_bits);
+  if (v->sym) {
+    gm_sym_free(v->g, &v->s_val);
+    gm_sym_free(v->g, &v->s_bits);
+    gm_sym_free(v->g, &v->s_alt);
+  } else {
+    cudaFree(v->x_val);
+    cudaFree(v->x_bits);
+    cudaFree(v->x_alt);
+  }
   cudaFree(v->y_val);
   cudaFree(v->y_bits);
   cudaFree(v->scratch);
+  for (void* p : v->retired) cudaFree(p);
   delete v;
   return 0;
 }
 extern "C" int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* o) {
+  memset(o, 0, sizeof *o);
   o->sizeof_T = v->sizeof_T;
   o->sizeof_U = v->sizeof_U;
   o->x_val = v->x_val;
   o->x_bits = v->x_bits;
   o->y_val = v->y_val;
   o->y_bits = v->y_bits;
+  o->x_alt = v->x_alt;
+  if (v->sym && v->g->world > 1) {
+    int np = 0;
+    for (int q = 0; q < v->g->world; q++)
+      if (q != v->g->rank) {
+        o->peer_x_val[np] = v->s_val.peer[q];
+        o->peer_x_bits[np] = (unsigned*)v->s_bits.peer[q];
+        o->peer_x_alt[np] = v->s_alt.peer[q];
+        np++;
+      }
+    o->n_peers = np;
+  }
   return 0;
 }
 
 extern "C" int gm_vectors_scratch(gm_vectors* v, long long bytes, void** out) {
   if ((size_t)bytes > v->scratch_bytes) {
-    cudaFree(v->scratch);
+    // cudaFree waits for the whole device: with several ranks in one process a peer may be spinning in the
+    // barrier kernel for THIS rank, so the old block is retired and freed with the vectors
+    if (v->scratch) v->retired.push_back(v->scratch);
     v->scratch = nullptr;
     v->scratch_bytes = 0;
-    CK(cudaMalloc(&v->scratch, (size_t)bytes));
-    v->scratch_bytes = (size_t)bytes;
+    const size_t want = (size_t)bytes + (size_t)bytes / 4;
+    CK(cudaMalloc(&v->scratch, want));
+    v->scratch_bytes = want;
   }
   *out = v->scratch;
   return 0;
@@ -1248,6 +1358,14 @@ extern "C" int gm_graph_exchange_x_parts(gm_graph* g, gm_vectors* v, int values,
   return 0;
 }
 extern "C" int gm_graph_exchange_x(gm_graph* g, gm_vectors* v) { return gm_graph_exchange_x_parts(g, v, 1, 1); }
+extern "C" int gm_graph_exchange_buffer(gm_graph* g, void* buf, long long bytes_per_rank) {
+  if (g->world == 1) return 0;
+  if (!g->allgather) {
+    gm_set_error("world > 1 but no exchange functions were registered (gm_graph_set_exchange)");
+    return 1;
+  }
+  return g->allgather(g->xctx, buf, bytes_per_rank, (void*)g->stream);
+}
 extern "C" int gm_graph_allreduce_or(gm_graph* g, int* flag) {
   if (g->world == 1) return 0;
   if (!g->allreduce_or) {

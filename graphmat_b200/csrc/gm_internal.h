@@ -15,6 +15,14 @@
 
 void gm_set_error(const std::string& s);
 
+// a buffer every rank allocates with the same size, with the other ranks' copies mapped here
+struct gm_sym {
+  void* local = nullptr;
+  void* peer[GM_MAX_WORLD] = {};  // indexed by rank; peer[my rank] == local
+  bool opened[GM_MAX_WORLD] = {};  // mapped through cudaIpcOpenMemHandle (to be closed)
+  size_t bytes = 0;
+};
+
 // one operand matrix (device memory owned here); see gm_matrix_view for the meaning
 struct gm_matrix {
   int n_slots = 0, n_heavy = 0, n_slices = 0, identity = 0, n_coop = 0, n_slices_wide = 0;
@@ -70,15 +78,33 @@ struct gm_graph {
   gm_allgather_fn allgather = nullptr;
   gm_allreduce_or_fn allreduce_or = nullptr;
   void* xctx = nullptr;
+  // peer memory (gm_peer.cu): the other ranks' buffers mapped into this process
+  bool peers_on = false;
+  gm_allgather_host_fn host_gather = nullptr;
+  void* host_ctx = nullptr;
+  gm_sym sync;              // 2 * GM_MAX_WORLD 64-bit words per rank: barrier flags (parity-alternated)
+  unsigned barrier_round = 0;
+  gm_sym sym_staging;       // public-order staging area for the *_slice accessors (peers only)
+  std::vector<void*> retired;  // outgrown scratch blocks, freed with the graph
 };
 
 struct gm_vectors {
   int sizeof_T = 0, sizeof_U = 0, n_full = 0, n_pad = 0;
+  gm_graph* g = nullptr;    // the graph these vectors were created for (stream, peers)
   void* x_val = nullptr;
   unsigned* x_bits = nullptr;
   void* y_val = nullptr;
   unsigned* y_bits = nullptr;
+  void* x_alt = nullptr;
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  std::vector<void*> retired;  // outgrown scratch blocks, freed with the vectors
+  bool sym = false;         // x_val / x_bits / x_alt are symmetric allocations mapped on every rank
+  gm_sym s_val, s_bits, s_alt;
 };
+
+// gm_peer.cu
+int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out);  // collective
+int gm_sym_free(gm_graph* g, gm_sym* s);                   // collective
+int gm_peer_copy_slice(gm_graph* g, gm_sym* s, size_t offset, size_t bytes);  // my [offset, +bytes) -> every peer, same offset
 #endif

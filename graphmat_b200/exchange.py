@@ -76,6 +76,31 @@ def attach(G, tmp, dist):
     G.set_exchange(capi.ALLGATHER_FN(ag), capi.ALLREDUCE_OR_FN(ar))
 
 
+def attach_peers(G, dist):
+    """Map every rank's buffers into every process (CUDA IPC over NVLink): after this the per-iteration
+    exchange is device stores + a barrier kernel, with no NCCL call and no Python in the loop.  The only
+    thing torch.distributed does is the one-time all-gather of the handle blobs.  Must be called before
+    the Vectors are created.  Returns False (graph unchanged) when peer mapping is not possible."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    on_gpu = dist.get_backend() == "nccl"
+
+    def gather(ctx, mine, all_, nbytes):
+        try:
+            src = torch.frombuffer((C.c_char * nbytes).from_address(mine), dtype=torch.uint8).clone()
+            out = torch.empty(world * nbytes, dtype=torch.uint8)
+            if on_gpu:
+                src, out = src.cuda(), out.cuda()
+            dist.all_gather_into_tensor(out, src)
+            C.memmove(all_, out.cpu().numpy().ctypes.data, world * nbytes)
+            return 0
+        except Exception as e:
+            print("graphmat_b200.exchange: host all-gather failed:", e)
+            return 1
+
+    return G.enable_peers(capi.ALLGATHER_HOST_FN(gather))
+
+
 class LocalRanks:
     """`world` ranks of one sharded graph inside one process / one GPU (test harness).
 
@@ -92,6 +117,33 @@ class LocalRanks:
         self.bufs = [None] * self.world
         for r, g in enumerate(graphs):
             g.set_exchange(capi.ALLGATHER_FN(self._make_ag(r)), capi.ALLREDUCE_OR_FN(self._make_ar(r)))
+
+    @classmethod
+    def with_peers(cls, graphs, make_vectors):
+        """The peer-memory exchange (gm_peer.cu) between ranks of ONE process: every rank's buffers are plain
+        device pointers for the others, the stores and the barrier kernel are the ones a multi-GPU run uses.
+        make_vectors(graph) -> Vectors is called on a thread per rank (vector creation is collective)."""
+        self = cls.__new__(cls)
+        import torch
+        self.torch = torch
+        self.world = len(graphs)
+        self.graphs = graphs
+        self.barrier = threading.Barrier(self.world)
+        self.blobs = [None] * self.world
+
+        def make_gather(r):
+            def gather(ctx, mine, all_, nbytes):
+                self.blobs[r] = C.string_at(mine, nbytes)
+                self.barrier.wait()
+                C.memmove(all_, b"".join(self.blobs), nbytes * self.world)
+                self.barrier.wait()
+                return 0
+            return gather
+        ok = self.run(lambda r: graphs[r].enable_peers(capi.ALLGATHER_HOST_FN(make_gather(r))))
+        if not all(ok):
+            raise RuntimeError("peer mapping failed inside one process")
+        self.vectors = self.run(lambda r: make_vectors(graphs[r]))
+        return self
 
     def _make_ag(self, r):
         torch = self.torch
@@ -122,6 +174,16 @@ class LocalRanks:
             flag[0] = v
             return 0
         return ar
+
+    def close(self):
+        """destroy the vectors, then the graphs (after every rank's work is done: see gm_sym_free)"""
+        for g in self.graphs:
+            g.synchronize()
+        for v in self.vectors:
+            for one in (v if isinstance(v, (tuple, list)) else (v,)):
+                one.close()
+        for g in self.graphs:
+            g.close()
 
     def run(self, fn):
         out = [None] * self.world

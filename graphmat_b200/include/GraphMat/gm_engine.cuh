@@ -88,6 +88,54 @@ __device__ __forceinline__ bool test_bit(const unsigned* __restrict__ bits, int 
   return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
 }
 
+// ------------------------------------------------------- fused apply + send --
+// ALL_VERTICES programs that do not override do_every_iteration and sweep ONE operand matrix
+// (PageRank): the thread that finishes a row's fold holds the reduced message in a register, so it
+// runs the apply loop body (GraphMatRuntime.h:201-213) and the next iteration's send_message
+// (GraphMatRuntime.h:79-85) right there.  y never goes to memory and there is no apply kernel.
+// The next message vector is a SECOND buffer (the pass still gathers from the current one); on a
+// sharded graph the same store also goes to every peer's copy of that buffer over NVLink (peer
+// memory), so the exchange of SURVEY 8e overlaps the pass row by row instead of following it.
+constexpr int GM_MAX_PEERS = GM_MAX_WORLD - 1;
+template <class T, class V>
+struct epilogue {
+  V* vp;                    // local vertex properties (placement order)
+  T* x_next;                // next message vector, local copy (n_full entries)
+  T* x_peer[GM_MAX_PEERS];  // the same buffer on the other ranks (n_peers valid entries)
+  int n_peers;
+  int x_off;                // rank * n_local_pad: this rank's slice of x
+  int n_valid;              // local vertices that exist (the rest is padding)
+  int* flag;                // "some vertex changed"
+};
+// returns "the vertex property changed" (the caller raises the flag: warp-aggregated where it can)
+template <class P, class T, class U, class V>
+__device__ __forceinline__ bool fused_apply_send(const prog_bytes<P>& pb, const epilogue<T, V>& ep, int vtx, bool have,
+                                                 const U& acc) {
+  if (vtx >= ep.n_valid) return false;
+  alignas(16) unsigned char pbuf[sizeof(P)];
+  memcpy(pbuf, pb.b, sizeof(P));
+  P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
+  V cur = ep.vp[vtx];
+  bool changed = false;
+  if (have) {  // apply runs only where a message arrived
+    V old = cur;
+    prog.P::apply(acc, cur);
+    changed = (old != cur);
+    ep.vp[vtx] = cur;
+  }
+  if (ep.x_next) {  // NULL: single-iteration run, nobody reads the next message vector
+    T t;
+    (void)prog.P::send_message(cur, t);  // the bool is ignored (GraphMatRuntime.h:79-85)
+    const size_t i = (size_t)ep.x_off + (size_t)vtx;
+    ep.x_next[i] = t;
+    for (int p = 0; p < ep.n_peers; p++) ep.x_peer[p][i] = t;
+  }
+  return changed;
+}
+__device__ __forceinline__ void raise_flag(int* flag) {
+  if (*((volatile int*)flag) == 0) atomicExch(flag, 1);
+}
+
 
 // ---- cache-hinted loads ------------------------------------------------------
 // The index/edge streams are read once per pass: keep them out of L1.  The message
@@ -128,10 +176,14 @@ template <class X>
 __device__ __forceinline__ X ld_gather(const X* x, int c, int hot_limit) {
   if constexpr (sizeof(X) == 4) {
     if (hot_limit == -1) return __ldg(x + c);
-    if (hot_limit < -1) {  // experiment only (GM_HOT_LIMIT=-K): what a perfect on-SM cache of K columns would buy
+#ifdef GM_EXPERIMENTS
+    if (hot_limit < -1) {  // GM_HOT_LIMIT=-K: what a perfect on-SM cache of K columns would buy (WRONG results)
       if (c < -hot_limit) return __ldg(x + (c & 63));  // always an L1 hit
       return __ldg(x + c);
     }
+#else
+    if (hot_limit < -1) return __ldg(x + c);
+#endif
     unsigned v;
     if (c < hot_limit) return __ldg(x + c);
     else asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(x + c));
@@ -242,11 +294,12 @@ __global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
 // Launch shape: block b, warp w folds slices [slice_begin + (8b + w) * spw, + spw).  Slices are
 // stored longest first and blocks are dispatched in order, so the hardware block scheduler gives
 // longest-processing-time-first load balance for free; spw > 1 only for the short-row tail.
-template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int UNROLL>
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int UNROLL,
+          bool EPI = false>
 __global__ void __launch_bounds__(256)
     k_sell(prog_bytes<P> pb, gm_matrix_view M, int slice_begin, int slice_end, int spw, int hot_limit,
            const T* __restrict__ x, const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
-           unsigned* __restrict__ ybits) {
+           unsigned* __restrict__ ybits, epilogue<T, V> ep = epilogue<T, V>()) {
   const P& prog = pb.get();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -269,7 +322,7 @@ __global__ void __launch_bounds__(256)
       if (have && len > 0) acc = y[vtx];
     }
     const int* cp = cols + base + lane;
-    const E* ep = vals + base + lane;
+    const E* evp = vals + base + lane;
     for (int i = 0; i < width; i += UNROLL) {
       int c[UNROLL];
       E ev[UNROLL];
@@ -280,7 +333,7 @@ __global__ void __launch_bounds__(256)
         on[u] = (i + u) < len;
         if (on[u]) {
           c[u] = ld_stream(cp + (long long)(i + u) * 32);
-          ev[u] = ld_stream(ep + (long long)(i + u) * 32);
+          ev[u] = ld_stream(evp + (long long)(i + u) * 32);
         }
       }
 #pragma unroll
@@ -304,12 +357,17 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
-    if (have && len > 0) y[vtx] = acc;
-    unsigned m = __ballot_sync(0xffffffffu, have);
-    if (IDENT) {
-      if (lane == 0) ybits[slot >> 5] = m;  // heavy and ELL slots never share a word
-    } else if (have && len > 0) {
-      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+    if constexpr (EPI) {
+      const bool ch = fused_apply_send<P, T, U, V>(pb, ep, vtx, have && len > 0, acc);
+      if (__ballot_sync(0xffffffffu, ch) != 0 && lane == 0) raise_flag(ep.flag);
+    } else {
+      if (have && len > 0) y[vtx] = acc;
+      unsigned m = __ballot_sync(0xffffffffu, have);
+      if (IDENT) {
+        if (lane == 0) ybits[slot >> 5] = m;  // heavy and ELL slots never share a word
+      } else if (have && len > 0) {
+        atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
+      }
     }
   }
 }
@@ -381,10 +439,12 @@ __global__ void __launch_bounds__(256)
 // 32 in flight, process_message runs on all lanes.  The fold of each batch is
 //   REORDER = false: lane 0 walks the batch left to right (exact serial order)
 //   REORDER = true : order-preserving pairwise tree (program declared associative)
-template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool REORDER>
+template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool REORDER,
+          bool EPI = false>
 __global__ void __launch_bounds__(128)
     k_heavy(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int hot_limit, const T* __restrict__ x,
-            const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits) {
+            const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
+            epilogue<T, V> ep = epilogue<T, V>()) {
   const P& prog = pb.get();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -397,8 +457,14 @@ __global__ void __launch_bounds__(128)
 
   for (int slot = row_begin + warp; slot < M.n_heavy; slot += nwarps) {
     const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
-    if (beg == end) continue;
     const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    if (beg == end) {  // padding slot of the heavy prefix
+      if constexpr (EPI) {
+        U none;
+        if (lane == 0 && fused_apply_send<P, T, U, V>(pb, ep, vtx, false, none)) raise_flag(ep.flag);
+      }
+      continue;
+    }
     V vprop;
     if (NEEDVP) vprop = vp[vtx];
     U acc;
@@ -461,109 +527,9 @@ __global__ void __launch_bounds__(128)
       }
       __syncwarp();
     }
-    if (lane == 0 && have) {
-      y[vtx] = acc;
-      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
-    }
-  }
-}
-
-
-// ------------------------------ SpMSpV: heavy rows, cooperative (reorderable) --
-// W warps fold one long row.  A lane owns 8 CONSECUTIVE entries (two 128-bit index
-// loads), folds them left to right, the warp combines its 32 partials with an
-// order-preserving tree in shared memory, and thread 0 appends the W warp partials in
-// order to the running value.  Only for programs whose reduce_function is associative.
-template <class P, class T, class U, class V, class E, bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, int W>
-__global__ void __launch_bounds__(W * 32)
-    k_heavy_coop(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit, const T* __restrict__ x,
-                 const unsigned* __restrict__ xbits, const V* __restrict__ vp, U* __restrict__ y,
-                 unsigned* __restrict__ ybits) {
-  const P& prog = pb.get();
-  extern __shared__ __align__(16) unsigned char smem[];
-  U* buf = reinterpret_cast<U*>(smem);  // W * 32 partials
-  __shared__ unsigned s_valid[W];
-  const int lane = threadIdx.x & 31;
-  const int w = threadIdx.x >> 5;
-  const int* __restrict__ cols = M.h_col;
-  const E* __restrict__ vals = reinterpret_cast<const E*>(M.h_val);
-  for (int slot = row_begin + blockIdx.x; slot < row_end; slot += gridDim.x) {
-    const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
-    if (beg == end) continue;
-    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
-    V vprop;
-    if (NEEDVP) vprop = vp[vtx];
-    U acc;  // thread 0
-    bool have = false;
-    if (ACCUM && threadIdx.x == 0) {
-      have = test_bit(ybits, vtx);
-      if (have) acc = y[vtx];
-    }
-    for (long long k0 = beg & ~7ll; k0 < end; k0 += W * 256) {
-      const long long i0 = k0 + w * 256 + lane * 8;
-      U part;
-      bool pv = false;
-      if (i0 < end && i0 + 8 > beg) {
-        int c[8];
-        E ev[8];
-        *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
-        *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
-#pragma unroll
-        for (int j = 0; j < 8; j++) ev[j] = ld_stream(vals + i0 + j);
-        T xv[8];
-        bool on[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          on[j] = (i0 + j >= beg) && (i0 + j < end);
-          if (on[j] && !ALLACT) on[j] = test_bit(xbits, c[j]);
-          if (on[j]) xv[j] = ld_gather(x, c[j], hot_limit);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if (on[j]) {
-            if (pv) {
-              U tmp;
-              prog.P::process_message(xv[j], ev[j], vprop, tmp);
-              prog.P::reduce_function(part, tmp);
-            } else {
-              prog.P::process_message(xv[j], ev[j], vprop, part);
-              pv = true;
-            }
-          }
-        }
-      }
-      U* wb = buf + w * 32;
-      if (pv) wb[lane] = part;
-      __syncwarp();
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned vm = __ballot_sync(0xffffffffu, pv);
-        if ((lane & (2 * d - 1)) == 0 && ((vm >> (lane + d)) & 1u)) {
-          if (pv) {
-            U a = wb[lane];
-            prog.P::reduce_function(a, wb[lane + d]);
-            wb[lane] = a;
-          } else {
-            wb[lane] = wb[lane + d];
-            pv = true;
-          }
-        }
-        __syncwarp();
-      }
-      if (lane == 0) s_valid[w] = pv ? 1u : 0u;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-#pragma unroll 1
-        for (int q = 0; q < W; q++) {
-          if (s_valid[q]) {
-            if (have) prog.P::reduce_function(acc, buf[q * 32]);
-            else { acc = buf[q * 32]; have = true; }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0 && have) {
+    if constexpr (EPI) {
+      if (lane == 0 && fused_apply_send<P, T, U, V>(pb, ep, vtx, have, acc)) raise_flag(ep.flag);
+    } else if (lane == 0 && have) {
       y[vtx] = acc;
       atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
     }
@@ -691,10 +657,11 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <class P, class U, bool IDENT, bool ACCUM>
+template <class P, class T, class U, class V, bool IDENT, bool ACCUM, bool EPI = false>
 __global__ void __launch_bounds__(128)
     k_heavy_combine(prog_bytes<P> pb, gm_matrix_view M, const U* __restrict__ partial,
-                    const unsigned char* __restrict__ pvalid, U* __restrict__ y, unsigned* __restrict__ ybits) {
+                    const unsigned char* __restrict__ pvalid, U* __restrict__ y, unsigned* __restrict__ ybits,
+                    epilogue<T, V> ep = epilogue<T, V>()) {
   const P& prog = pb.get();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -703,8 +670,14 @@ __global__ void __launch_bounds__(128)
   const int row = blockIdx.x * 4 + wib;
   if (row >= M.n_heavy) return;
   const int s0 = __ldg(M.seg_ptr + row), s1 = __ldg(M.seg_ptr + row + 1);
-  if (s0 == s1) return;
   const int vtx = IDENT ? row : __ldg(M.slot_vertex + row);
+  if (s0 == s1) {  // empty row inside the heavy prefix
+    if constexpr (EPI) {
+      U none;
+      if (lane == 0 && fused_apply_send<P, T, U, V>(pb, ep, vtx, false, none)) raise_flag(ep.flag);
+    }
+    return;
+  }
   const int run = (s1 - s0 + 31) >> 5;
   int k = s0 + lane * run;
   const int kend = min(k + run, s1);
@@ -717,7 +690,13 @@ __global__ void __launch_bounds__(128)
     }
   }
   warp_ordered_tree<U, P>(prog, wb, part, pv, lane);
-  if (lane == 0 && pv) {
+  if constexpr (EPI) {
+    if (lane == 0) {
+      U r;
+      if (pv) r = wb[0];
+      if (fused_apply_send<P, T, U, V>(pb, ep, vtx, pv, r)) raise_flag(ep.flag);
+    }
+  } else if (lane == 0 && pv) {
     if (ACCUM && test_bit(ybits, vtx)) {
       U a = y[vtx];
       prog.P::reduce_function(a, wb[0]);
@@ -730,7 +709,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------ SpMSpV: heavy rows, exact fp32 + (gm_fadd32_exact) --
-// Same data movement as k_heavy_coop; the fold is the bit-exact parallel evaluation of
+// A lane owns 8 CONSECUTIVE entries (two 128-bit index loads); the fold is the bit-exact parallel evaluation of
 // the serial fp32 sum (gm_fadd32.cuh).  W = 1: one warp per row, several rows per block.
 // W > 1: the block folds W*256 addends per round.  Every warp scans its 256 under the
 // binade of the block's entry value; warp 0 scans the W warp totals and finds the first
@@ -758,11 +737,12 @@ __global__ void __launch_bounds__(256)
   for (int j = 0; j < 8; j++) staged[i0 + j] = v[j];
 }
 
-template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W, bool STAGED = false>
+template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W, bool STAGED = false, bool EPI = false>
 __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit,
                    const T* __restrict__ x, const unsigned* __restrict__ xbits, float* __restrict__ y,
-                   unsigned* __restrict__ ybits, const T* __restrict__ staged = nullptr) {
+                   unsigned* __restrict__ ybits, const T* __restrict__ staged = nullptr,
+                   epilogue<T, V> ep = epilogue<T, V>()) {
   const P& prog = pb.get();
   constexpr int WPB = (W == 1) ? 4 : W;  // warps per block
   __shared__ float sm_s;
@@ -886,13 +866,20 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
       }
     }
     if (W == 1) {
-      if (lane == 0 && have) {
+      if constexpr (EPI) {
+        if (lane == 0 && fused_apply_send<P, T, float, V>(pb, ep, vtx, have, s)) raise_flag(ep.flag);
+      } else if (lane == 0 && have) {
         y[vtx] = s;
         atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
       }
     } else {
       __syncthreads();
-      if (threadIdx.x == 0 && sm_have) {
+      if constexpr (EPI) {
+        if (threadIdx.x == 0) {
+          const float r = sm_s;
+          if (fused_apply_send<P, T, float, V>(pb, ep, vtx, sm_have != 0, r)) raise_flag(ep.flag);
+        }
+      } else if (threadIdx.x == 0 && sm_have) {
         y[vtx] = sm_s;
         atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
       }
@@ -900,10 +887,6 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     }
   }
 }
-
-}  // namespace gm
-#include "gm_pass.cuh"
-namespace gm {
 
 // ------------------------------------------------------------------ driver --
 #define GM_CUDA_OK(call)                                                                      \
@@ -915,10 +898,6 @@ namespace gm {
       return 1;                                                                               \
     }                                                                                         \
   } while (0)
-
-#ifndef GM_DEFAULT_PASS_HOT
-#define GM_DEFAULT_PASS_HOT 0
-#endif
 
 // ---------------------------------------------- SpMSpV: sparse frontier (push) --
 // The reference's my_spmspv walks only the columns whose x bit is set (spmspv.h:55-63): its work is
@@ -1088,6 +1067,7 @@ struct engine {
   typedef typename types::Um U;
   typedef typename types::Vp V;
   typedef typename types::Ev E;
+  typedef epilogue<T, V> EP;
   static constexpr bool REORDER = is_reorderable<P>::value;
 
   static int check(const gm_graph_view& gv, const gm_vectors_view& vv) {
@@ -1115,96 +1095,92 @@ struct engine {
   // heavy rows.  fp32-sum programs: exact parallel fold, [0, n_coop) one thread block per row,
   // [n_coop, n_heavy) one warp per row.  Associative programs: two-phase segmented fold.
   // Anything else: one warp per row, batches folded serially (exact for any reduce_function).
-  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+  // EPI: the kernel that finishes a row also applies and sends (fused_apply_send); y is not written.
+  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool EPI>
   static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, int hot, const T* x, const unsigned* xbits,
-                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc, gm_vectors* vecs) {
+                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc, gm_vectors* vecs,
+                        const EP& ep) {
     constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
-    static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
     if constexpr (FADD) {
       const int n_coop = M.n_coop;
       int coop_begin = 0;
       if constexpr (ALLACT && sizeof(T) == 4) {
         // the longest rows: gathers by the whole GPU into a staging array, then one block per row folds from it
         static const bool no_stage = getenv("GM_NO_STAGE") != nullptr;
-        if (M.n_long > 0 && !no_stage && !(dbg & 1)) {
+        if (M.n_long > 0 && !no_stage) {
           void* scratch = nullptr;
           if (gm_vectors_scratch(vecs, (M.long_entries + 64) * (long long)sizeof(T), &scratch)) return 1;
           T* staged = (T*)scratch;
           const long long groups = (M.long_entries + 7) / 8;
           k_stage_rows<T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(M.h_col, M.long_entries, x, hot, staged);
           // 32 warps per row: rounds of 8192 addends halve the number of serial rounds of the longest row
-          k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 32, true><<<M.n_long, 32 * 32, 0, st>>>(pb, M, 0, M.n_long, hot, x, xbits,
-                                                                                          (float*)y, ybits, staged);
+          k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 32, true, EPI><<<M.n_long, 32 * 32, 0, st>>>(
+              pb, M, 0, M.n_long, hot, x, xbits, (float*)y, ybits, staged, ep);
           if (sc) sc->launches += 2;
           coop_begin = M.n_long;
         }
       }
-      if (n_coop > coop_begin && !(dbg & 1)) {
-        int blocks = n_coop - coop_begin < 148 * 64 ? n_coop - coop_begin : 148 * 64;
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16><<<blocks, 16 * 32, 0, st>>>(pb, M, coop_begin, n_coop, hot, x, xbits, (float*)y, ybits);
+      if (n_coop > coop_begin) {
+        const int cap = gm_sm_count() * 64;
+        int blocks = n_coop - coop_begin < cap ? n_coop - coop_begin : cap;
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16, false, EPI><<<blocks, 16 * 32, 0, st>>>(
+            pb, M, coop_begin, n_coop, hot, x, xbits, (float*)y, ybits, nullptr, ep);
         if (sc) sc->launches++;
       }
-      if (M.n_heavy > n_coop && !(dbg & 2)) {
+      if (M.n_heavy > n_coop) {
         int rows = M.n_heavy - n_coop;
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1><<<(rows + 3) / 4, 128, 0, st>>>(pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits);
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1, false, EPI><<<(rows + 3) / 4, 128, 0, st>>>(
+            pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits, nullptr, ep);
         if (sc) sc->launches++;
       }
     } else if constexpr (REORDER) {
-      if (M.n_segs > 0 && !(dbg & 1)) {
+      if (M.n_segs > 0 || EPI) {
         void* scratch = nullptr;
         const size_t pbytes = ((size_t)M.n_segs * sizeof(U) + 255) & ~(size_t)255;
-        if (gm_vectors_scratch(vecs, (long long)(pbytes + M.n_segs), &scratch)) return 1;
+        if (gm_vectors_scratch(vecs, (long long)(pbytes + M.n_segs + 256), &scratch)) return 1;
         U* partial = (U*)scratch;
         unsigned char* pvalid = (unsigned char*)scratch + pbytes;
         const size_t sh = 4 * 32 * sizeof(U);
         constexpr bool LASTW = is_last_writer<P>::value && !ALLACT;
-        k_heavy_seg<P, T, U, V, E, ALLACT, NEEDVP, IDENT, LASTW><<<(M.n_segs + 3) / 4, 128, sh, st>>>(pb, M, hot, x, xbits, vp, partial, pvalid);
-        k_heavy_combine<P, U, IDENT, ACCUM><<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, partial, pvalid, y, ybits);
+        auto kseg = k_heavy_seg<P, T, U, V, E, ALLACT, NEEDVP, IDENT, LASTW>;
+        auto kcmb = k_heavy_combine<P, T, U, V, IDENT, ACCUM, EPI>;
+        if (big_smem(kseg, sh) || big_smem(kcmb, sh)) return 1;
+        if (M.n_segs > 0) kseg<<<(M.n_segs + 3) / 4, 128, sh, st>>>(pb, M, hot, x, xbits, vp, partial, pvalid);
+        kcmb<<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, partial, pvalid, y, ybits, ep);
         if (sc) sc->launches += 2;
       }
     } else {
-      if (!(dbg & 1)) {
-        size_t sh = 4 * 32 * sizeof(U);
-        k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, false><<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, 0, hot, x, xbits, vp, y, ybits);
-        if (sc) sc->launches++;
-      }
+      size_t sh = 4 * 32 * sizeof(U);
+      auto kh = k_heavy<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, false, EPI>;
+      if (big_smem(kh, sh)) return 1;
+      kh<<<(M.n_heavy + 3) / 4, 128, sh, st>>>(pb, M, 0, hot, x, xbits, vp, y, ybits, ep);
+      if (sc) sc->launches++;
     }
     return 0;
   }
 
-  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM>
+  // kernels whose dynamic shared memory is 128 reduced messages: above the 48 KB default (sizeof(U) > 384,
+  // e.g. LatentVector<K> with K >= 48) the limit is raised explicitly, and refused beyond the hardware's 227 KB
+  template <class K>
+  static int big_smem(K kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    if (bytes > 227 * 1024) {
+      fprintf(stderr, "graphmat_b200: reduced message type of %zu bytes is too large for the long-row kernels\n", sizeof(U));
+      return 1;
+    }
+    GM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+  }
+
+  template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool EPI>
   static int mult_t(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
-                    step_counters* sc, gm_vectors* vecs) {
+                    step_counters* sc, gm_vectors* vecs, const EP& ep) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     const T* x = (const T*)vv.x_val;
     const V* vp = (const V*)gv.vertexproperty;
     U* y = (U*)vv.y_val;
     prog_bytes<P> pb = pack(prog);
     const int hot = gv.hot_limit;
-    // fp32-sum programs: the whole pass as one persistent kernel with a shared-memory copy of the
-    // hottest columns of x (gm_pass.cuh); GM_PASS_HOT = bytes of shared memory per SM, 0 = separate kernels
-    if constexpr (is_fadd32<P>::value && std::is_same<T, float>::value && std::is_same<U, float>::value && !NEEDVP &&
-                  !ACCUM) {
-      static const int pass_bytes = getenv("GM_PASS_HOT") ? atoi(getenv("GM_PASS_HOT")) : GM_DEFAULT_PASS_HOT;
-      static const int pass_min = getenv("GM_PASS_MIN_SLICES") ? atoi(getenv("GM_PASS_MIN_SLICES")) : 148 * 64;
-      if (pass_bytes > 0 && M.n_slices >= pass_min) {
-        int hot_n = pass_bytes / (int)sizeof(T);
-        if (hot_n > gv.n_full) hot_n = gv.n_full;
-        hot_n &= ~3;
-        auto kern = k_pass_fadd32<P, T, V, E, ALLACT, IDENT>;
-        static bool attr_set = false;
-        if (!attr_set) {
-          GM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          attr_set = true;
-        }
-        int* counters = gv.d_flags + 4;
-        GM_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
-        kern<<<gm_sm_count(), 1024, (size_t)hot_n * sizeof(T), st>>>(pb, M, hot_n, 32, counters, x, vv.x_bits, (float*)y, vv.y_bits);
-        if (sc) { sc->launches++; sc->edges += M.nnz; }
-        GM_CUDA_OK(cudaGetLastError());
-        return 0;
-      }
-    }
     // sparse frontier: walk only the active columns when they hold few entries (push, see k_push_expand)
     if constexpr (!ALLACT && sizeof(U) <= 16 && sizeof(E) == 4) {
       const int push_div = gv.push_divisor;  // 0: never
@@ -1236,8 +1212,10 @@ struct engine {
           k_push_fold<P, U, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, MP, n_ent, plan.keys, plan.order, (const U*)plan.vals, y,
                                                                   vv.y_bits, n_long, long_runs);
           const int lb = gm_sm_count() * 4;
-          k_push_fold_long<P, U, IDENT, ACCUM, REORDER><<<lb, 128, 4 * 32 * sizeof(U), st>>>(
-              pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y, vv.y_bits);
+          auto kfl = k_push_fold_long<P, U, IDENT, ACCUM, REORDER>;
+          if (big_smem(kfl, 4 * 32 * sizeof(U))) return 1;
+          kfl<<<lb, 128, 4 * 32 * sizeof(U), st>>>(pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y,
+                                                   vv.y_bits);
           if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; }
           GM_CUDA_OK(cudaGetLastError());
           return 0;
@@ -1252,10 +1230,10 @@ struct engine {
       GM_CUDA_OK(cudaStreamWaitEvent(sh, (cudaEvent_t)gv.ev_fork, 0));
     }
     if (M.n_heavy > 0) {
-      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc, vecs)) return 1;
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM, EPI>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc, vecs, ep))
+        return 1;
     }
-    static const int dbg = getenv("GM_DEBUG_SKIP") ? atoi(getenv("GM_DEBUG_SKIP")) : 0;
-    if (M.n_slices > 0 && !(dbg & 4)) {
+    if (M.n_slices > 0) {
       // wide slices: one per warp, deep unroll (a lane's chain waits for loads once per UNROLL
       // steps); narrow tail: several slices per warp so blocks stay worth their launch
       constexpr int UW = (sizeof(T) <= 8 && sizeof(U) <= 8) ? 16 : 1;
@@ -1268,8 +1246,8 @@ struct engine {
           k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(nw + 7) / 8, 256, 0, st>>>(
               pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
         else
-          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW><<<(nw + 7) / 8, 256, 0, st>>>(
-              pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
+          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW, EPI><<<(nw + 7) / 8, 256, 0, st>>>(
+              pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits, ep);
         if (sc) sc->launches++;
       }
       if (M.n_slices > nw) {
@@ -1278,8 +1256,8 @@ struct engine {
           k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(warps + 7) / 8, 256, 0, st>>>(
               pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
         else
-          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN><<<(warps + 7) / 8, 256, 0, st>>>(
-              pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
+          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN, EPI><<<(warps + 7) / 8, 256, 0, st>>>(
+              pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits, ep);
         if (sc) sc->launches++;
       }
     }
@@ -1293,11 +1271,25 @@ struct engine {
   }
 
   // mult_segment / mult_segment3 for one operand matrix   SPMV.h:62-95
+  // ep != nullptr: fused apply+send epilogue (only all-active, single-operand passes)
   static int mult(const P& prog, const gm_graph_view& gv, const gm_matrix_view& M, const gm_vectors_view& vv,
-                  bool allact, bool accum, step_counters* sc, gm_vectors* vecs) {
+                  bool allact, bool accum, step_counters* sc, gm_vectors* vecs, const EP* ep = nullptr) {
     const bool needvp = prog.getProcessMessageRequiresVertexprop();
     const bool ident = M.identity != 0;
-#define GM_MULT(A_, N_, I_, C_) return mult_t<A_, N_, I_, C_>(prog, gv, M, vv, sc, vecs)
+    const EP none = EP();
+    if (ep) {
+      if (!allact || accum) {
+        fprintf(stderr, "graphmat_b200: fused epilogue on a pass that is not all-active / single-operand\n");
+        return 1;
+      }
+      if (needvp) {
+        if (ident) return mult_t<true, true, true, false, true>(prog, gv, M, vv, sc, vecs, *ep);
+        return mult_t<true, true, false, false, true>(prog, gv, M, vv, sc, vecs, *ep);
+      }
+      if (ident) return mult_t<true, false, true, false, true>(prog, gv, M, vv, sc, vecs, *ep);
+      return mult_t<true, false, false, false, true>(prog, gv, M, vv, sc, vecs, *ep);
+    }
+#define GM_MULT(A_, N_, I_, C_) return mult_t<A_, N_, I_, C_, false>(prog, gv, M, vv, sc, vecs, none)
 #define GM_MULT_C(A_, N_, I_) \
   do { if (accum) GM_MULT(A_, N_, I_, true); else GM_MULT(A_, N_, I_, false); } while (0)
 #define GM_MULT_I(A_, N_) \
@@ -1315,12 +1307,12 @@ struct engine {
 
   // SpMTSpV / SpMSpV selection   GraphMatRuntime.h:160-176
   static int spmspv(const P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, bool allact, step_counters* sc,
-                    gm_vectors* vecs) {
+                    gm_vectors* vecs, const EP* ep = nullptr) {
     cudaStream_t st = (cudaStream_t)gv.stream;
-    GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
     const int order = (int)prog.getOrder();
-    if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc, vecs);
-    if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc, vecs);
+    if (!ep) GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
+    if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc, vecs, ep);
+    if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc, vecs, ep);
     if (order == GraphMat::ALL_EDGES) {
       if (mult(prog, gv, gv.AT, vv, allact, false, sc, vecs)) return 1;
       return mult(prog, gv, gv.A, vv, allact, true, sc, vecs);
@@ -1364,29 +1356,65 @@ struct engine {
     return 0;
   }
 
+  // The exchange of SURVEY 8e: every rank's slice of x (values and/or bit words) reaches every rank.
+  //   peers mapped (gm_graph_enable_peers): one kernel stores the slice into every peer's x -- dense for
+  //     all-active programs, bit words + ACTIVE values only otherwise -- then the barrier kernel;
+  //   else the host-supplied all-gather callbacks (NCCL through torch.distributed).
+  // Every iteration of a sharded run ends with a barrier, so nobody still gathers from x when this overwrites it.
+  static int exchange(gm_graph* g, gm_vectors* tmp, const gm_vectors_view& vv, bool dense, bool bits, step_counters* sc) {
+    if (vv.n_peers > 0) {
+      if (gm_graph_push_x(g, tmp, dense ? 1 : 0)) return 1;
+      if (gm_graph_peer_barrier(g, 0)) return 1;
+      if (sc) sc->launches += 2;
+      return 0;
+    }
+    return gm_graph_exchange_x_parts(g, tmp, 1, bits ? 1 : 0);
+  }
+
+  // events / vectors the run owns: released on every exit path
+  struct run_guard {
+    cudaEvent_t e0 = nullptr, e1 = nullptr, s0 = nullptr, s1 = nullptr;
+    std::vector<cudaEvent_t> evs;
+    gm_vectors* own = nullptr;
+    ~run_guard() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (s0) cudaEventDestroy(s0);
+      if (s1) cudaEventDestroy(s1);
+      for (auto& e : evs) cudaEventDestroy(e);
+      if (own) gm_vectors_destroy(own);
+    }
+  };
+
   // run_graph_program   GraphMatRuntime.h:93-279
   static int run(P& prog, gm_graph* g, int iterations, gm_vectors* tmp, gm_run_stats* stats) {
     gm_graph_view gv;
     if (gm_graph_view_get(g, &gv)) return 1;
-    gm_vectors* own = nullptr;
+    run_guard rg;
     if (!tmp) {
-      if (gm_vectors_create(&own, g, (int)sizeof(T), (int)sizeof(U))) return 1;
-      tmp = own;
+      if (gm_vectors_create(&rg.own, g, (int)sizeof(T), (int)sizeof(U))) return 1;
+      tmp = rg.own;
     }
     gm_vectors_view vv;
     if (gm_vectors_view_get(tmp, &vv)) return 1;
     if (check(gv, vv)) return 1;
     cudaStream_t st = (cudaStream_t)gv.stream;
     step_counters sc;
-    cudaEvent_t e0, e1, s0, s1;
-    GM_CUDA_OK(cudaEventCreate(&e0));
-    GM_CUDA_OK(cudaEventCreate(&e1));
-    GM_CUDA_OK(cudaEventCreate(&s0));
-    GM_CUDA_OK(cudaEventCreate(&s1));
+    GM_CUDA_OK(cudaEventCreate(&rg.e0));
+    GM_CUDA_OK(cudaEventCreate(&rg.e1));
+    GM_CUDA_OK(cudaEventCreate(&rg.s0));
+    GM_CUDA_OK(cudaEventCreate(&rg.s1));
     float ms_spmv = 0.f;
     const bool all = prog.getActivity() == GraphMat::ALL_VERTICES;
     const bool fuse = all && NO_HOOK && !getenv("GM_NO_FUSE");
-    GM_CUDA_OK(cudaEventRecord(e0, st));
+    // fused apply+send epilogue: one operand matrix per pass, so the thread that ends a row's fold owns its message
+    const bool epi = fuse && (int)prog.getOrder() != GraphMat::ALL_EDGES && !getenv("GM_NO_EPILOGUE");
+    const bool peers = vv.n_peers > 0;
+    if (epi && iterations != 1) {
+      if (gm_vectors_need_alt(tmp)) return 1;
+      if (gm_vectors_view_get(tmp, &vv)) return 1;
+    }
+    GM_CUDA_OK(cudaEventRecord(rg.e0, st));
     if (all && set_all_active(gv, &sc)) return 1;
     int it = 0, converged = 1;
     // Fixed iteration count and no do_every_iteration hook: nothing on the host depends on the
@@ -1395,7 +1423,7 @@ struct engine {
     // the flag of the last iteration is read once at the end.
     const bool async = iterations > 0 && NO_HOOK && !getenv("GM_SYNC_LOOP");
     constexpr int EV_BATCH = 64;
-    std::vector<cudaEvent_t> evs;
+    std::vector<cudaEvent_t>& evs = rg.evs;
     const bool timing = stats != nullptr;
     auto harvest = [&](int count) -> int {
       if (count <= 0) return 0;
@@ -1408,24 +1436,59 @@ struct engine {
       return 0;
     };
     if (async && timing) {
-      evs.resize(2 * (size_t)std::min(iterations, EV_BATCH));
+      evs.resize(2 * (size_t)std::min(iterations, EV_BATCH), nullptr);
       for (auto& e : evs) GM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDefault));
     }
     int pending = 0;
+    void* xbuf[2] = {vv.x_val, vv.x_alt};
+    int cur = 0;
     while (1) {
       GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
-      if (!(fuse && it > 0) && send(prog, gv, vv, &sc)) return 1;  // fused: the previous apply already sent
-      // fused ALL_VERTICES programs re-arm every x bit in every iteration: the bit words are exchanged once
-      if (gv.world > 1 && gm_graph_exchange_x_parts(g, tmp, 1, (fuse && it > 0) ? 0 : 1)) return 1;
-      cudaEvent_t es0 = s0, es1 = s1;
+      gm_vectors_view vc = vv;  // this iteration's message vector
+      vc.x_val = xbuf[cur];
+      EP ep;
+      if (epi) {
+        if (it == 0) {
+          if (send(prog, gv, vv, &sc)) return 1;
+          if (gv.world > 1 && exchange(g, tmp, vv, true, true, &sc)) return 1;
+          // rows without entries are never visited by the pass: their (constant) message is copied once
+          if (xbuf[1]) GM_CUDA_OK(cudaMemcpyAsync(xbuf[1], xbuf[0], (size_t)gv.n_full * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        }
+        void* const* peer_next = cur == 0 ? vv.peer_x_alt : vv.peer_x_val;
+        ep.vp = (V*)gv.vertexproperty;
+        ep.x_next = xbuf[1] ? (T*)xbuf[cur ^ 1] : nullptr;  // single iteration: the next message is never read
+        ep.n_peers = (peers && xbuf[1]) ? vv.n_peers : 0;
+        for (int q = 0; q < ep.n_peers; q++) ep.x_peer[q] = (T*)peer_next[q];
+        ep.x_off = gv.rank * gv.n_local_pad;
+        ep.n_valid = gv.n_local;
+        ep.flag = gv.d_flags;
+      } else {
+        if (!(fuse && it > 0) && send(prog, gv, vv, &sc)) return 1;  // fused: the previous apply already sent
+        // fused ALL_VERTICES programs re-arm every x bit in every iteration: the bit words are exchanged once
+        if (gv.world > 1 && exchange(g, tmp, vv, all, !(fuse && it > 0), &sc)) return 1;
+      }
+      cudaEvent_t es0 = rg.s0, es1 = rg.s1;
       if (async && timing) {
         es0 = evs[2 * pending];
         es1 = evs[2 * pending + 1];
       }
       if (timing) GM_CUDA_OK(cudaEventRecord(es0, st));
-      if (spmspv(prog, gv, vv, all, &sc, tmp)) return 1;
+      if (spmspv(prog, gv, vc, all, &sc, tmp, epi ? &ep : nullptr)) return 1;
       if (timing) GM_CUDA_OK(cudaEventRecord(es1, st));
-      if (apply(prog, gv, vv, &sc, fuse)) return 1;
+      if (epi) {
+        if (xbuf[1]) {
+          if (gv.world > 1 && !peers && gm_graph_exchange_buffer(g, xbuf[cur ^ 1], (long long)gv.n_local_pad * sizeof(T))) return 1;
+          cur ^= 1;
+        }
+      } else {
+        if (apply(prog, gv, vv, &sc, fuse)) return 1;
+      }
+      // every iteration of a run over mapped peers ends with the barrier: it orders the stores into the
+      // peers' buffers before their next pass, and it ORs the "changed" flag on the device
+      if (peers && gv.world > 1) {
+        if (gm_graph_peer_barrier(g, 1)) return 1;
+        sc.launches++;
+      }
       if (async) {
         if (timing && ++pending == EV_BATCH) {
           if (harvest(pending)) return 1;
@@ -1435,11 +1498,11 @@ struct engine {
         GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         GM_CUDA_OK(cudaStreamSynchronize(st));
         int changed = gv.h_flags[0];
-        if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
+        if (gv.world > 1 && !peers && gm_graph_allreduce_or(g, &changed)) return 1;
         converged = !changed;
         if (timing) {
           float t;
-          GM_CUDA_OK(cudaEventElapsedTime(&t, s0, s1));
+          GM_CUDA_OK(cudaEventElapsedTime(&t, rg.s0, rg.s1));
           ms_spmv += t;
           static const bool trace = getenv("GM_TRACE_ITERS") != nullptr;
           if (trace)
@@ -1453,20 +1516,27 @@ struct engine {
       if (it == iterations) break;
       if (iterations <= 0 && converged) break;
     }
+    if (epi && cur == 1) {
+      // leave the latest message vector where the separate steps (gm_step_*) and the next run expect it
+      GM_CUDA_OK(cudaMemcpyAsync(xbuf[0], xbuf[1], (size_t)gv.n_full * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    }
     if (async) {
       GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
       if (timing && harvest(pending)) return 1;
       GM_CUDA_OK(cudaStreamSynchronize(st));
       int changed = gv.h_flags[0];
-      if (gv.world > 1 && gm_graph_allreduce_or(g, &changed)) return 1;
+      if (gv.world > 1 && !peers && gm_graph_allreduce_or(g, &changed)) return 1;
       converged = !changed;
-      for (auto& e : evs) cudaEventDestroy(e);
     }
-    GM_CUDA_OK(cudaEventRecord(e1, st));
-    GM_CUDA_OK(cudaEventSynchronize(e1));
+    GM_CUDA_OK(cudaEventRecord(rg.e1, st));
+    GM_CUDA_OK(cudaEventSynchronize(rg.e1));
+    if (peers && gv.h_flags[15]) {
+      fprintf(stderr, "graphmat_b200: a peer did not reach the barrier (timeout)\n");
+      return 1;
+    }
     if (stats) {
       float t;
-      GM_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+      GM_CUDA_OK(cudaEventElapsedTime(&t, rg.e0, rg.e1));
       stats->iterations = it;
       stats->converged = converged;
       stats->ms_total = t;
@@ -1475,11 +1545,6 @@ struct engine {
       stats->edges_processed = sc.edges;
       stats->push_passes = sc.push_passes;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(s0);
-    cudaEventDestroy(s1);
-    if (own) gm_vectors_destroy(own);
     return 0;
   }
 };

@@ -96,10 +96,18 @@ typedef struct gm_graph_view {
   long long push_min_nnz;       /* ... and the matrix holds at least this many entries */
 } gm_graph_view;
 
+#define GM_MAX_WORLD 16
 typedef struct gm_vectors_view {
   int sizeof_T, sizeof_U;
   void* x_val; unsigned int* x_bits;  /* n_full entries: the all-gathered message vector */
   void* y_val; unsigned int* y_bits;  /* n_local_pad entries */
+  void* x_alt;                        /* second message buffer of the fused apply+send pass (NULL until
+                                         gm_vectors_need_alt): the pass gathers from one and writes the other */
+  int n_peers;                        /* > 0: the message buffers of the other ranks are mapped into this
+                                         process (gm_graph_enable_peers) and the kernels store into them */
+  void* peer_x_val[GM_MAX_WORLD - 1];
+  void* peer_x_alt[GM_MAX_WORLD - 1];
+  unsigned int* peer_x_bits[GM_MAX_WORLD - 1];
 } gm_vectors_view;
 
 typedef struct gm_run_stats {
@@ -170,6 +178,36 @@ int gm_graph_exchange_x(gm_graph* g, gm_vectors* v);     /* all-gather x values 
 int gm_graph_exchange_x_parts(gm_graph* g, gm_vectors* v, int values, int bits); /* ... either half alone: an
                                                             ALL_VERTICES program's bit words never change after iteration 0 */
 int gm_graph_allreduce_or(gm_graph* g, int* flag);       /* "some vertex changed" across ranks */
+int gm_graph_exchange_buffer(gm_graph* g, void* buf, long long bytes_per_rank); /* all-gather of any buffer of
+                                                            world equal slices (the second message buffer) */
+
+/* ---- peer memory: the exchange without a library call per iteration.  Every rank maps the message
+ *      buffers, the vertex-property staging area and a small flag array of every other rank (CUDA IPC
+ *      between processes, plain pointers between ranks of one process) and the kernels store straight
+ *      into them over NVLink: the fused apply+send pass writes each new message to all ranks as it
+ *      finishes a row, ACTIVE_ONLY programs push the bit words and only the ACTIVE values of their slice
+ *      (the (index,value) wire format of include/GMDP/vectors/DenseSegment.h:532-538,665-700, with the bit
+ *      words as the index list), and a one-block barrier kernel (release/acquire flags in peer memory)
+ *      orders the iterations and ORs the "changed" flag.  The host language only supplies a blocking
+ *      all-gather of small HOST blobs for the one-time handle exchange (torch.distributed, MPI_Allgather).
+ *      Collective: every rank must call gm_graph_enable_peers, and afterwards gm_vectors_create /
+ *      gm_vectors_destroy / gm_run_program / gm_graph_{set,get}_vertexproperties_slice, in the same order.
+ *      Returns non-zero (and leaves the graph on the callback exchange) if a peer cannot be mapped. */
+typedef int (*gm_allgather_host_fn)(void* ctx, const void* mine, void* all, int bytes_per_rank);
+int gm_graph_enable_peers(gm_graph* g, gm_allgather_host_fn allgather_host, void* ctx);
+int gm_graph_peers_enabled(const gm_graph* g);
+int gm_graph_peer_barrier(gm_graph* g, int or_changed_flag); /* enqueue the barrier kernel on the graph's stream;
+                                                            or_changed_flag: d_flags[0] becomes its OR over ranks */
+int gm_graph_push_x(gm_graph* g, gm_vectors* v, int dense); /* store this rank's slice of x (bit words + values,
+                                                            dense != 0: every value, else only where the bit is set)
+                                                            into every peer's x; no barrier */
+int gm_vectors_need_alt(gm_vectors* v);                  /* allocate x_alt (collective when peers are enabled) */
+/* Distributed Graph::setVertexproperty / getVertexproperty for all vertices: rank r passes / receives only the
+ * contiguous public ids [slice_begin(r), slice_begin(r+1)) of gm_graph_slice_begin (host memory), 1/world of the PCIe traffic of the
+ * whole-array calls; the redistribution to the owning ranks runs over peer memory. */
+long long gm_graph_slice_begin(const gm_graph* g, int rank);
+int gm_graph_set_vertexproperties_slice(gm_graph* g, const void* slice_values);
+int gm_graph_get_vertexproperties_slice(gm_graph* g, void* slice_values);
 
 /* ---- sparse frontiers: push SpMSpV over the active columns only.  The reference's my_spmspv visits only
  *      columns whose x bit is set (include/GMDP/singlenode/spmspv.h:55-63), so its work is proportional to

@@ -18,13 +18,43 @@ def available(app="pagerank"):
     return os.path.exists(os.path.join(_HERE, "_ref", "libgm_ref_%s.so" % app))
 
 
+def _cpu_has_avx512():
+    try:
+        flags = open("/proc/cpuinfo").read().split("flags", 1)[1].split("\n", 1)[0].split()
+        return all(f in flags for f in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+    except Exception:
+        return False
+
+
+def build_flavour(app="pagerank"):
+    """which build of the reference library this host gets (oracle/Makefile)"""
+    v4 = os.path.join(_HERE, "_ref", "libgm_ref_%s_v4.so" % app)
+    if os.path.exists(v4) and _cpu_has_avx512() and not os.environ.get("GM_REF_NO_AVX512"):
+        return "x86-64-v4", v4
+    return "x86-64-v3", os.path.join(_HERE, "_ref", "libgm_ref_%s.so" % app)
+
+
 def _lib(app):
     if app not in _libs:
-        path = os.path.join(_HERE, "_ref", "libgm_ref_%s.so" % app)
+        path = build_flavour(app)[1]
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
         _libs[app] = C.CDLL(path)
     return _libs[app]
+
+
+def rmat_edges(scale, edge_factor=16, seed=1, weight_max=0, weight_seed=2):
+    """The synthetic RMAT input of SURVEY 8(d) from oracle/librmat.so (no product code involved)."""
+    path = os.path.join(_HERE, "librmat.so")
+    if "rmat" not in _libs:
+        _libs["rmat"] = C.CDLL(path)
+    nnz = edge_factor << scale
+    src = np.empty(nnz, np.int32)
+    dst = np.empty(nnz, np.int32)
+    val = np.empty(nnz, np.int32)
+    _libs["rmat"].gmo_rmat_edges(C.c_int(scale), C.c_int(edge_factor), C.c_ulonglong(seed), C.c_int(weight_max),
+                                 C.c_ulonglong(weight_seed), _p(src), _p(dst), _p(val))
+    return 1 << scale, src, dst, val
 
 
 def _i32(a):
@@ -112,6 +142,7 @@ class PageRankSession:
         L = _lib("pagerank")
         L.gm_ref_pagerank_open.restype = C.c_void_p
         self.threads = threads
+        self.n = n
         self.nnz = len(src)
         self.h = C.c_void_p(L.gm_ref_pagerank_open(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src),
                                                    _p(dst), _p(val)))
@@ -121,6 +152,13 @@ class PageRankSession:
         ms = C.c_double()
         it = _lib("pagerank").gm_ref_pagerank_run(self.h, C.c_int(self.threads), C.c_int(iterations), C.byref(ms))
         return it, ms.value
+
+    def get(self):
+        """-> (pagerank f32[n], degree i32[n]) as the last run left them"""
+        pr = np.empty(self.n, np.float32)
+        deg = np.empty(self.n, np.int32)
+        _lib("pagerank").gm_ref_pagerank_get(self.h, _p(pr), _p(deg))
+        return pr, deg
 
     def close(self):
         if self.h:

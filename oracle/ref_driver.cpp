@@ -160,6 +160,15 @@ int gm_ref_pagerank_run(void* h, int threads, int iterations, double* ms) {
   GraphMat::graph_program_clear(pr_tmp);
   return pr.iters;
 }
+// the ranks and degrees as the last run left them (bench.py compares the GPU engine with them)
+void gm_ref_pagerank_get(void* h, float* pagerank, int* degree) {
+  RefPageRankSession* s = (RefPageRankSession*)h;
+  for (int i = 1; i <= s->G.getNumberOfVertices(); i++) {
+    PR p = s->G.getVertexproperty(i);
+    pagerank[i - 1] = p.pagerank;
+    degree[i - 1] = p.degree;
+  }
+}
 void gm_ref_pagerank_close(void* h) { delete (RefPageRankSession*)h; }
 #endif
 

@@ -27,7 +27,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert "workload" in d["config"] and "sample" in d["config"] and d["config"]["sample_scale"] == 12
+    assert d["warmup"] == 1
+    # the reference arm never loads the product library (its input comes from oracle/librmat.so)
+    assert d["repo_libs_loaded"] and all(l.startswith("oracle/") for l in d["repo_libs_loaded"])
 
 
 def test_reference_arm_other_ranks_exit_quietly():

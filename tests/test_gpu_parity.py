@@ -344,3 +344,27 @@ def test_staged_long_rows_pagerank(monkeypatch):
     a = apps.pagerank(n, None, None, graph=Gd, iterations=8)
     b = port.pagerank(n, s, d, None, threads=4, iterations=8)
     assert (a[1] == b[1]).all() and (a[0] == b[0]).all()
+
+
+def test_pagerank_unfused_paths(monkeypatch):
+    """The fused apply+send epilogue is the default for PageRank; the separate apply kernel (with and without the
+    fused send) must give the same bits."""
+    g = load("rmat12_t4")
+    n, s, d, _ = util.rmat_numpy(12)
+    for env in ("GM_NO_EPILOGUE", "GM_NO_FUSE"):
+        monkeypatch.setenv(env, "1")
+        pr10, deg, _ = apps.pagerank(n, s, d, None, iterations=10, threads=4, heavy_threshold=16)
+        pr, _, it = apps.pagerank(n, s, d, None, threads=4)
+        monkeypatch.delenv(env)
+        assert (pr10 == g["pagerank10"]).all() and (deg == g["degree"]).all()
+        assert (pr == g["pagerank"]).all() and it == int(g["pr_iterations"])
+
+
+def test_bad_edge_ids_are_refused():
+    """an id outside [1, n] must come back as an error, not as an out-of-bounds write on the device."""
+    s = np.array([1, 2, 9], np.int32)
+    d = np.array([2, 3, 1], np.int32)
+    with pytest.raises(RuntimeError, match="outside"):
+        capi.Graph.from_edges(8, s, d, None, capi.PR_DTYPE)
+    with pytest.raises(RuntimeError, match="outside"):
+        capi.Graph.from_edges(8, d, np.array([0, 1, 2], np.int32), None, capi.PR_DTYPE)

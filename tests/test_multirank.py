@@ -178,3 +178,115 @@ def test_sharded_engine_one_gpu(world, push):
     for r in range(world):
         graphs[r].get_vertexproperties(out)
     assert (out["depth"] == od).all() and (out["parent"] == op).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_engine_peer_memory(world):
+    """The peer-memory exchange (gm_peer.cu): fused apply+send stores into every rank's message buffer,
+    sparse push of ACTIVE_ONLY frontiers, the barrier kernel with the OR of the changed flags, and the
+    distributed (slice) vertex-property accessors -- ranks inside one process on one GPU."""
+    from graphmat_b200 import apps, capi, exchange
+    n, s, d, v = util.rmat_numpy(12, weight_max=127)
+    src0 = util.first_source(s)
+    threads = 4
+    mk = lambda dt, **kw: [capi.Graph.from_edges(n, s, d, kw.pop("val", None), dt, threads=threads, rank=r, world=world,
+                                                 heavy_threshold=64, coop_threshold=512) for r in range(world)]
+    # ---- PageRank: fixed iterations (async loop) and until convergence ----
+    graphs = mk(capi.PR_DTYPE)
+    lr = exchange.LocalRanks.with_peers(graphs, lambda g: (capi.Vectors(g, capi.PROG_DEGREE), capi.Vectors(g, capi.PROG_PAGERANK)))
+    assert all(g.peers_enabled() for g in graphs)
+    init = np.zeros(n, capi.PR_DTYPE)
+    init["pagerank"] = 0.3
+    for iters in (10, capi.UNTIL_CONVERGENCE):
+        def run_pr(r):
+            g = graphs[r]
+            lo, hi = g.slice_range(r)
+            g.set_vertexproperties_slice(init[lo:hi])
+            g.set_all_active()
+            g.run(capi.PROG_DEGREE, None, 1, lr.vectors[r][0])
+            g.set_all_active()
+            st = g.run(capi.PROG_PAGERANK, capi.PageRankState(0.3), iters, lr.vectors[r][1])
+            return st.iterations, g.get_vertexproperties_slice(r)
+        res = lr.run(run_pr)
+        opr, odeg, oit = port.pagerank(n, s, d, None, threads=threads, iterations=iters)
+        assert [r[0] for r in res] == [oit] * world
+        out = np.concatenate([r[1] for r in res])
+        assert len(out) == n and (out["degree"] == odeg).all()
+        assert (out["pagerank"] == opr).all()
+    lr.close()
+    # ---- BFS (sparse frontier: bit words + active values) and SSSP, pull and push passes ----
+    for push in (False, True):
+        graphs = mk(capi.BFS_DTYPE)
+        for g in graphs:
+            g.set_push_policy(1, 0) if push else g.set_push_policy(0, 0)
+        lr = exchange.LocalRanks.with_peers(graphs, lambda g: capi.Vectors(g, capi.PROG_BFS))
+        vp = np.zeros(n, capi.BFS_DTYPE)
+        vp["depth"] = 0xFFFFFFFF
+        vp["parent"] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        vp["id"] = np.arange(1, n + 1, dtype=np.uint64)
+        vp["depth"][src0 - 1] = 0
+
+        def prep_bfs(r):
+            # building the column-major companion frees device memory (cudaFree waits for the whole device): with
+            # all ranks in one process it must not overlap another rank's barrier kernel, so it is its own phase
+            g = graphs[r]
+            if push:
+                g.push_ready(1)
+            lo, hi = g.slice_range(r)
+            g.set_vertexproperties_slice(vp[lo:hi])
+            g.synchronize()
+
+        def run_bfs(r):
+            g = graphs[r]
+            g.set_all_inactive()
+            g.set_active(src0)
+            it = g.run(capi.PROG_BFS, capi.BFSState(1), capi.UNTIL_CONVERGENCE, lr.vectors[r]).iterations
+            return it, g.get_vertexproperties_slice(r)
+        lr.run(prep_bfs)
+        res = lr.run(run_bfs)
+        od, op, oit, _ = port.bfs(n, s, d, src0, threads=threads)
+        assert [r[0] for r in res] == [oit] * world
+        out = np.concatenate([r[1] for r in res])
+        assert (out["depth"] == od).all() and (out["parent"] == op).all()
+        lr.close()
+    graphs = mk(capi.SSSP_DTYPE, val=v)
+    lr = exchange.LocalRanks.with_peers(graphs, lambda g: capi.Vectors(g, capi.PROG_SSSP))
+
+    def run_sssp(r):
+        g = graphs[r]
+        inf = np.zeros(1, capi.SSSP_DTYPE)
+        inf["distance"] = 0xFFFFFFFF
+        g.set_all_vertexproperty(inf[0])
+        g.set_all_inactive()
+        g.set_vertexproperty(src0, np.zeros(1, capi.SSSP_DTYPE)[0])
+        g.set_active(src0)
+        it = g.run(capi.PROG_SSSP, None, capi.UNTIL_CONVERGENCE, lr.vectors[r]).iterations
+        return it, g.get_vertexproperties_slice(r)
+    res = lr.run(run_sssp)
+    odist, osit, _ = port.sssp(n, s, d, v, src0, threads=threads)
+    assert [r[0] for r in res] == [osit] * world
+    assert (np.concatenate([r[1] for r in res])["distance"] == odist).all()
+    lr.close()
+    # ---- SGD (ALL_EDGES: separate apply kernel, dense push of 264-byte messages) ----
+    u, it_, r_ = util.ratings(300, 60, 4000)
+    nv, K = 360, 32
+    dt = capi.latent_dtype(K)
+    p_sgd, _ = capi.SGD_PROGRAMS[K]
+    graphs = [capi.Graph.from_edges(nv, u, it_, r_, dt, threads=threads, rank=r, world=world) for r in range(world)]
+    lr = exchange.LocalRanks.with_peers(graphs, lambda g: capi.Vectors(g, p_sgd))
+    vp = np.zeros(nv, dt)
+    vp["lv"] = apps.sgd_init(nv, K)
+
+    def run_sgd(r):
+        g = graphs[r]
+        lo, hi = g.slice_range(r)
+        g.set_vertexproperties_slice(vp[lo:hi])
+        g.set_all_active()
+        g.run(p_sgd, capi.SGDState(0.001, 0.00000035), 10, lr.vectors[r])
+        return g.get_vertexproperties_slice(r)
+    out = np.concatenate(lr.run(run_sgd))
+    olv, _, _ = port.sgd(300, 360, u, it_, r_, K=K, iterations=10, threads=threads)
+    err = np.abs(out["lv"] - olv) / np.maximum(np.abs(olv), 1e-300)
+    assert err.max() <= 1e-6
+    lr.close()
