@@ -89,35 +89,62 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms; nvidia-smi as fallback)"""
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.sm_max = [], 0, None
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        if self.nvml is not None:
+            nv = self.nvml
+            while not self.stop_flag:
+                try:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
+        q = "clocks.sm,clocks.max.sm"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.rows.append(f)
+                if len(f) >= 2 and f[0].isdigit():
+                    self.sm.append(int(f[0]))
+                    self.sm_max = int(f[1])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        sm = sorted(self.sm)
+        names = []
+        if self.nvml is not None:
+            nv = self.nvml
+            for bit, name in ((getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                              (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                              (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                              (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")):
+                if self.reasons & bit:
+                    names.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": names, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@ libgraphmat_b200.so, and a missing library or a non-zero status raises.
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -113,7 +114,7 @@ SYMBOLS = [
     "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts", "gm_abi_struct_sizes",
     "gm_graph_exchange_buffer", "gm_graph_enable_peers", "gm_graph_peers_enabled", "gm_graph_peer_barrier",
     "gm_graph_push_x", "gm_vectors_need_alt", "gm_graph_slice_begin", "gm_graph_set_vertexproperties_slice",
-    "gm_graph_get_vertexproperties_slice",
+    "gm_graph_get_vertexproperties_slice", "gm_vectors_aux",
 ]
 
 
@@ -168,6 +169,7 @@ class Graph:
         self.h = handle
         self.vdtype = np.dtype(vdtype)
         self._keep = []
+        self._vectors = weakref.WeakSet()  # gm_vectors point back at their graph: they go first
 
     @staticmethod
     def _opts(threads, rank, world, heavy_threshold, order_like, build_mask, on_device=False, coop_threshold=0):
@@ -203,6 +205,8 @@ class Graph:
 
     def close(self):
         if self.h:
+            for v in list(self._vectors):
+                v.close()
             lib().gm_graph_destroy(self.h)
             self.h = None
 
@@ -352,6 +356,7 @@ class Vectors:
         self.h = C.c_void_p()
         self.graph = graph
         _check(lib().gm_vectors_create(C.byref(self.h), graph.h, sT, sU), "gm_vectors_create")
+        graph._vectors.add(self)
 
     def view(self):
         v = VectorsView()

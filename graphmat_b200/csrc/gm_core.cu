@@ -1298,6 +1298,7 @@ extern "C" int gm_vectors_destroy(gm_vectors* v) {
   cudaFree(v->y_val);
   cudaFree(v->y_bits);
   cudaFree(v->scratch);
+  cudaFree(v->aux);
   for (void* p : v->retired) cudaFree(p);
   delete v;
   return 0;
@@ -1337,6 +1338,19 @@ extern "C" int gm_vectors_scratch(gm_vectors* v, long long bytes, void** out) {
     v->scratch_bytes = want;
   }
   *out = v->scratch;
+  return 0;
+}
+
+extern "C" int gm_vectors_aux(gm_vectors* v, long long bytes, void** out) {
+  if ((size_t)bytes > v->aux_bytes) {
+    if (v->aux) v->retired.push_back(v->aux);
+    v->aux = nullptr;
+    v->aux_bytes = 0;
+    CK(cudaMalloc(&v->aux, (size_t)bytes));
+    CK(cudaMemsetAsync(v->aux, 0xff, (size_t)bytes, v->g->stream));
+    v->aux_bytes = (size_t)bytes;
+  }
+  *out = v->aux;
   return 0;
 }
 

@@ -80,6 +80,7 @@ struct gm_graph {
   void* xctx = nullptr;
   // peer memory (gm_peer.cu): the other ranks' buffers mapped into this process
   bool peers_on = false;
+  bool peers_same_process = false;  // some peer is a rank of this process (test harness): barriers meet on the host
   gm_allgather_host_fn host_gather = nullptr;
   void* host_ctx = nullptr;
   gm_sym sync;              // 2 * GM_MAX_WORLD 64-bit words per rank: barrier flags (parity-alternated)
@@ -98,6 +99,8 @@ struct gm_vectors {
   void* x_alt = nullptr;
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* aux = nullptr;      // persistent second block (gm_vectors_aux)
+  size_t aux_bytes = 0;
   std::vector<void*> retired;  // outgrown scratch blocks, freed with the vectors
   bool sym = false;         // x_val / x_bits / x_alt are symmetric allocations mapped on every rank
   gm_sym s_val, s_bits, s_alt;

@@ -179,6 +179,7 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
   for (int q = 0; q < g->world && !bad; q++) {
     if (q == g->rank) continue;
     if (all[q].pid == mine.pid) {  // a rank of this process: its pointer is valid here
+      g->peers_same_process = true;
       if (all[q].device != mine.device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(all[q].device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) bad = 1;
@@ -251,6 +252,33 @@ extern "C" int gm_graph_peer_barrier(gm_graph* g, int or_changed_flag) {
   if (!g->peers_on) {
     gm_set_error("gm_graph_peer_barrier: peers are not enabled");
     return 1;
+  }
+  if (g->peers_same_process) {
+    // Ranks of ONE process share one device context: a device memory allocation or a shared hardware queue
+    // between the streams makes "kernel of rank B waits behind the spinning kernel of rank A" possible (implicit
+    // synchronization, CUDA programming guide 3.2.8.5.3), which would deadlock the device-side barrier.  The
+    // single-process harness (tests) therefore meets on the host; one process per GPU uses the kernel below.
+    CK(cudaStreamSynchronize(g->stream));
+    if (g->aux_stream) CK(cudaStreamSynchronize(g->aux_stream));
+    int mine = 0;
+    if (or_changed_flag) {
+      CK(cudaMemcpyAsync(g->h_flags + 14, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+      CK(cudaStreamSynchronize(g->stream));
+      mine = g->h_flags[14];
+    }
+    std::vector<int> all(g->world, 0);
+    if (g->host_gather(g->host_ctx, &mine, all.data(), (int)sizeof(int))) {
+      gm_set_error("peer memory: the host all-gather callback failed");
+      return 1;
+    }
+    if (or_changed_flag) {
+      int any = 0;
+      for (int q = 0; q < g->world; q++) any |= all[q];
+      g->h_flags[14] = any;
+      CK(cudaMemcpyAsync(g->d_flags, g->h_flags + 14, sizeof(int), cudaMemcpyHostToDevice, g->stream));
+      CK(cudaStreamSynchronize(g->stream));
+    }
+    return 0;
   }
   ptr_table t;
   for (int q = 0; q < GM_MAX_WORLD; q++) t.p[q] = q < g->world ? g->sync.peer[q] : nullptr;

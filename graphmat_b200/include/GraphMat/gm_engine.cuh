@@ -62,6 +62,13 @@ template <class P, class = void>
 struct is_last_writer : std::false_type {};
 template <class P>
 struct is_last_writer<P, typename std::enable_if<P::gm_last_writer>::type> : std::true_type {};
+// `static const bool gm_atomic_min = true;`: U is a 32-bit unsigned integer and reduce_function(a, b) is
+// a = min(a, b) (SSSP, DeltaStepping): commutative and associative, so a sparse-frontier pass may fold with
+// atomicMin straight into y instead of sorting its contributions.
+template <class P, class = void>
+struct is_atomic_min : std::false_type {};
+template <class P>
+struct is_atomic_min<P, typename std::enable_if<P::gm_atomic_min>::type> : std::true_type {};
 // `static const bool gm_fadd32_exact = true;`: T = U = float, process_message is
 // res = message, reduce is a += b and messages are >= 0.  Long rows then use the
 // bit-exact parallel emulation of the serial fp32 fold (k_heavy_fadd32).
@@ -223,11 +230,19 @@ __global__ void __launch_bounds__(256) k_send(prog_bytes<P> pb, int n_pad, const
 // (send_message on the fresh property) and re-arms the active set: one sweep over the vertex
 // properties per iteration instead of three kernels.
 constexpr int GM_APPLY_VPT = 4;  // vertices per thread: all loads of the 4 are issued before any is consumed
-template <class P, class T, class U, class V, bool FUSE>
-__global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, int n_pad, const U* __restrict__ y,
+// c_ptr != NULL (ACTIVE_ONLY programs with the column-major companion built, one GPU): the vertices that change
+// here ARE the next frontier, so the number of matrix entries their columns hold -- what decides between the
+// sparse-frontier and the row-major pass -- is summed into next_entries and travels to the host with the
+// "changed" flag: no separate counting kernel and no second host round trip per iteration.
+// RESET (gm_atomic_min programs): y is handed back holding the identity of min wherever a message was
+// consumed, so the next sparse pass can atomicMin into it without clearing the whole vector.
+template <class P, class T, class U, class V, bool FUSE, bool RESET = false>
+__global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, int n_pad, U* __restrict__ y,
                                                const unsigned* __restrict__ ybits, V* __restrict__ vp,
                                                unsigned* __restrict__ active, int* __restrict__ flags,
-                                               T* __restrict__ x, unsigned* __restrict__ xbits) {
+                                               T* __restrict__ x, unsigned* __restrict__ xbits,
+                                               const long long* __restrict__ c_ptr = nullptr,
+                                               unsigned long long* __restrict__ next_entries = nullptr, int x_off = 0) {
   alignas(16) unsigned char pbuf[sizeof(P)];
   memcpy(pbuf, pb.b, sizeof(P));
   P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
     }
   }
   bool any = false;
+  unsigned long long ents = 0;
 #pragma unroll
   for (int k = 0; k < VPT; k++) {
     const int i = base + k * 256;
@@ -257,6 +273,11 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
       prog.P::apply(msg[k], cur[k]);
       changed = (old != cur[k]);
       vp[i] = cur[k];
+      if constexpr (RESET) {
+        static_assert(sizeof(U) == 4, "gm_atomic_min programs reduce 32-bit unsigned messages");
+        reinterpret_cast<unsigned*>(y)[i] = 0xffffffffu;
+      }
+      if (!FUSE && changed && c_ptr) ents += (unsigned long long)(__ldg(c_ptr + x_off + i + 1) - __ldg(c_ptr + x_off + i));
     }
     if (FUSE && touch[k]) {
       T t;
@@ -276,6 +297,10 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
     }
   }
   if (any && *((volatile int*)flags) == 0) atomicExch(flags, 1);
+  if (!FUSE && c_ptr) {
+    for (int o = 16; o; o >>= 1) ents += __shfl_down_sync(0xffffffffu, ents, o);
+    if ((threadIdx.x & 31) == 0 && ents) atomicAdd(next_entries, ents);
+  }
 }
 
 __global__ void k_fill_bits(unsigned* bits, int n_valid, int n_pad) {
@@ -1042,6 +1067,87 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------- SpMSpV: sparse frontier without a sort (atomic push) --
+// For programs whose reduce is min (gm_atomic_min) or "last writer" (gm_last_writer) the sorted triples of the
+// path above are unnecessary:
+//   MODE 2 (min): every entry of an active column does atomicMin(y[row], process_message(...)); y holds the
+//     identity 0xffffffff wherever its bit is clear (k_apply<RESET> keeps that invariant).
+//   MODE 0 + MODE 1 (last writer): the left fold in ascending column order keeps the contribution with the
+//     LARGEST fold position among the active entries of the row.  Pass 0 takes atomicMax(win[row], position);
+//     pass 1 walks the same entries again and the one whose position won writes y[row] (and hands win[row]
+//     back as -1).  Positions are unique within a row, so exactly one entry writes: the same bits as the fold.
+// Work split: a warp takes 32 bit words of x; every active column with at most GM_PUSH_BIG entries is walked
+// by the whole warp, longer ones are queued and walked by the whole grid (k_push_atomic_big).
+constexpr int GM_PUSH_BIG = 2048;
+template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
+__device__ __forceinline__ void push_entry(const P& prog, const gm_matrix_view& M, long long e, const T& xv,
+                                           const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
+                                           int* __restrict__ win) {
+  const int slot = __ldg(M.c_row + e);
+  if constexpr (MODE == 0) {
+    atomicMax(win + slot, __ldg(M.c_rank + e));
+  } else {
+    if constexpr (MODE == 1) {
+      if (win[slot] != __ldg(M.c_rank + e)) return;
+      win[slot] = -1;
+    }
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    V vprop;
+    if (NEEDVP) vprop = vp[vtx];
+    U out;
+    prog.P::process_message(xv, __ldg(reinterpret_cast<const E*>(M.c_val) + e), vprop, out);
+    if constexpr (MODE == 1) y[vtx] = out;
+    else atomicMin(reinterpret_cast<unsigned*>(y) + vtx, *reinterpret_cast<const unsigned*>(&out));
+    const unsigned bit = 1u << (vtx & 31);
+    if (!(ybits[vtx >> 5] & bit)) atomicOr(ybits + (vtx >> 5), bit);
+  }
+}
+template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
+__global__ void __launch_bounds__(256)
+    k_push_atomic(prog_bytes<P> pb, gm_matrix_view M, int n_words, const unsigned* __restrict__ xbits,
+                  const T* __restrict__ x, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
+                  int* __restrict__ win, int* __restrict__ n_big, int* __restrict__ big_cols, int queue_big) {
+  const P& prog = pb.get();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int w = warp * 32 + lane;
+  unsigned word = w < n_words ? __ldg(xbits + w) : 0u;
+  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    lanes &= lanes - 1;
+    unsigned m = __shfl_sync(0xffffffffu, word, src);
+    const int cbase = (warp * 32 + src) * 32;
+    while (m) {
+      const int c = cbase + __ffs(m) - 1;
+      m &= m - 1;
+      const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
+      if (end - beg > GM_PUSH_BIG) {
+        if (queue_big && lane == 0) big_cols[atomicAdd(n_big, 1)] = c;
+        continue;
+      }
+      if (beg == end) continue;
+      const T xv = x[c];
+      for (long long e = beg + lane; e < end; e += 32) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
+    }
+  }
+}
+template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
+__global__ void __launch_bounds__(256)
+    k_push_atomic_big(prog_bytes<P> pb, gm_matrix_view M, const int* __restrict__ n_big, const int* __restrict__ big_cols,
+                      const T* __restrict__ x, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
+                      int* __restrict__ win) {
+  const P& prog = pb.get();
+  const int nb = *n_big;
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = gridDim.x * (long long)blockDim.x;
+  for (int k = 0; k < nb; k++) {
+    const int c = big_cols[k];
+    const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
+    const T xv = x[c];
+    for (long long e = beg + g; e < end; e += stride) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
+  }
+}
+
 inline int gm_sm_count() {
   static int n = 0;
   if (!n) {
@@ -1058,6 +1164,7 @@ struct step_counters {
   long long edges = 0;
   long long push_passes = 0;
   long long last_frontier_cols = -1, last_frontier_entries = -1;  // of the latest sparse pass (trace only)
+  long long next_entries = -1;  // entries of the coming pass's frontier when k_apply counted them (-1: unknown)
 };
 
 template <class P>
@@ -1181,15 +1288,17 @@ struct engine {
     U* y = (U*)vv.y_val;
     prog_bytes<P> pb = pack(prog);
     const int hot = gv.hot_limit;
-    // sparse frontier: walk only the active columns when they hold few entries (push, see k_push_expand)
+    // sparse frontier: walk only the active columns when they hold few entries (push)
     if constexpr (!ALLACT && sizeof(U) <= 16 && sizeof(E) == 4) {
       const int push_div = gv.push_divisor;  // 0: never
       const long long push_min = gv.push_min_nnz;
       if (push_div > 0 && M.nnz >= push_min && gv.owner) {
         const int which = (&M == &gv.A) ? 0 : 1;
-        int n_act = 0;
-        long long n_ent = 0;
-        if (gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+        int n_act = -1;
+        long long n_ent = sc ? sc->next_entries : -1;  // counted by the previous k_apply (one GPU)
+        if (n_ent < 0 || !M.c_ptr) {
+          if (gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+        }
         if (sc) { sc->last_frontier_cols = n_act; sc->last_frontier_entries = n_ent; }
         if (n_ent * push_div <= M.nnz) {
           if (n_ent == 0) {  // nothing arrives: y stays cleared
@@ -1199,26 +1308,65 @@ struct engine {
           gm_graph_view gv2;
           if (gm_graph_view_get(gv.owner, &gv2)) return 1;  // the companion may just have been built
           const gm_matrix_view& MP = which == 0 ? gv2.A : gv2.AT;
-          gm_push_plan plan;
-          if (gm_push_prepare(gv.owner, which, vecs, n_act, n_ent, &plan)) return 1;
-          const unsigned blocks = (unsigned)((n_ent + 255) / 256);
-          k_push_expand<P, T, U, V, E, NEEDVP, IDENT><<<blocks, 256, 0, st>>>(pb, MP, n_act, n_ent, plan.f_col, plan.f_off, x, vp,
-                                                                              plan.keys, plan.order, (U*)plan.vals);
-          if (gm_push_sort(gv.owner, &plan)) return 1;
-          // the long-run queue reuses the spare key buffer (at most n_ent / 17 runs of 2 entries each)
-          int* n_long = gv.d_flags + 13;
-          long long* long_runs = reinterpret_cast<long long*>(plan.keys_alt);
-          GM_CUDA_OK(cudaMemsetAsync(n_long, 0, sizeof(int), st));
-          k_push_fold<P, U, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, MP, n_ent, plan.keys, plan.order, (const U*)plan.vals, y,
-                                                                  vv.y_bits, n_long, long_runs);
-          const int lb = gm_sm_count() * 4;
-          auto kfl = k_push_fold_long<P, U, IDENT, ACCUM, REORDER>;
-          if (big_smem(kfl, 4 * 32 * sizeof(U))) return 1;
-          kfl<<<lb, 128, 4 * 32 * sizeof(U), st>>>(pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y,
-                                                   vv.y_bits);
-          if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; }
-          GM_CUDA_OK(cudaGetLastError());
-          return 0;
+          constexpr bool LASTW = is_last_writer<P>::value;
+          constexpr bool AMIN = is_atomic_min<P>::value && sizeof(U) == 4;
+          bool sorted_path = true;
+          if constexpr (!ACCUM && (LASTW || AMIN)) sorted_path = getenv("GM_NO_ATOMIC_PUSH") != nullptr;  // tests
+          if constexpr (!ACCUM && (LASTW || AMIN)) if (!sorted_path) {
+            // no sort, no host round trip: atomicMin into y, or "largest fold position wins" in two sweeps
+            void *aux = nullptr, *scratch = nullptr;
+            if (LASTW && gm_vectors_aux(vecs, (long long)MP.n_slots * 4, &aux)) return 1;
+            if (gm_vectors_scratch(vecs, (MP.nnz / GM_PUSH_BIG + 2) * 4, &scratch)) return 1;
+            int* win = (int*)aux;
+            int* big_cols = (int*)scratch;
+            int* n_big = gv.d_flags + 13;
+            GM_CUDA_OK(cudaMemsetAsync(n_big, 0, sizeof(int), st));
+            const int n_words = gv.n_full >> 5;
+            const unsigned blocks = (unsigned)(((n_words + 31) / 32 + 7) / 8);
+            const unsigned bigb = (unsigned)gm_sm_count() * 4;
+            if constexpr (LASTW) {
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 0><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, win, n_big, big_cols, 1);
+              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 0><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, win);
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 1><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, win, n_big, big_cols, 0);
+              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 1><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, win);
+              if (sc) sc->launches += 4;
+            } else {
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 2><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, nullptr, n_big, big_cols, 1);
+              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 2><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, nullptr);
+              if (sc) sc->launches += 2;
+            }
+            if (sc) { sc->edges += n_ent; sc->push_passes++; }
+            GM_CUDA_OK(cudaGetLastError());
+            return 0;
+          }
+          if (sorted_path) {
+            // any other reduce_function: (row, fold position, value) triples, radix-sorted, folded in the reference's order
+            if (n_act < 0 && gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+            if (n_ent == 0) {
+              if (sc) sc->push_passes++;
+              return 0;
+            }
+            gm_push_plan plan;
+            if (gm_push_prepare(gv.owner, which, vecs, n_act, n_ent, &plan)) return 1;
+            const unsigned blocks = (unsigned)((n_ent + 255) / 256);
+            k_push_expand<P, T, U, V, E, NEEDVP, IDENT><<<blocks, 256, 0, st>>>(pb, MP, n_act, n_ent, plan.f_col, plan.f_off, x, vp,
+                                                                                plan.keys, plan.order, (U*)plan.vals);
+            if (gm_push_sort(gv.owner, &plan)) return 1;
+            // the long-run queue reuses the spare key buffer (at most n_ent / 17 runs of 2 entries each)
+            int* n_long = gv.d_flags + 13;
+            long long* long_runs = reinterpret_cast<long long*>(plan.keys_alt);
+            GM_CUDA_OK(cudaMemsetAsync(n_long, 0, sizeof(int), st));
+            k_push_fold<P, U, IDENT, ACCUM><<<blocks, 256, 0, st>>>(pb, MP, n_ent, plan.keys, plan.order, (const U*)plan.vals, y,
+                                                                    vv.y_bits, n_long, long_runs);
+            const int lb = gm_sm_count() * 4;
+            auto kfl = k_push_fold_long<P, U, IDENT, ACCUM, REORDER>;
+            if (big_smem(kfl, 4 * 32 * sizeof(U))) return 1;
+            kfl<<<lb, 128, 4 * 32 * sizeof(U), st>>>(pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y,
+                                                     vv.y_bits);
+            if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; }
+            GM_CUDA_OK(cudaGetLastError());
+            return 0;
+          }
         }
       }
     }
@@ -1331,17 +1479,30 @@ struct engine {
     return (n + per - 1) / per;
   }
   // the apply loop   GraphMatRuntime.h:184-226 (flag = !converged)
-  static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc, bool fuse_send = false) {
+  static int apply(P& prog, const gm_graph_view& gv, const gm_vectors_view& vv, step_counters* sc, bool fuse_send = false,
+                   bool count_next = false, bool* counted = nullptr) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     const int n = gv.n_local_pad;
     T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
     unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
-    if (fuse_send)
-      k_apply<P, T, U, V, true><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
-                                                                (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
-    else
-      k_apply<P, T, U, V, false><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (const U*)vv.y_val, vv.y_bits,
-                                                                 (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
+    constexpr bool RESET = is_atomic_min<P>::value && sizeof(U) == 4;
+    if (fuse_send) {
+      k_apply<P, T, U, V, true, RESET><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (U*)vv.y_val, vv.y_bits,
+                                                                       (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb);
+    } else {
+      // the vertices that change are the next frontier: count the entries of their columns on the way (one GPU,
+      // single-operand ACTIVE_ONLY programs with the column-major companion built)
+      const long long* c_ptr = nullptr;
+      const int order = (int)prog.getOrder();
+      if (count_next && gv.world == 1 && order != GraphMat::ALL_EDGES)
+        c_ptr = order == GraphMat::OUT_EDGES ? gv.AT.c_ptr : gv.A.c_ptr;
+      unsigned long long* next = reinterpret_cast<unsigned long long*>(gv.d_flags + 10);
+      if (c_ptr) GM_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+      k_apply<P, T, U, V, false, RESET><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (U*)vv.y_val, vv.y_bits,
+                                                                        (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb,
+                                                                        c_ptr, next, gv.rank * n);
+      if (counted) *counted = c_ptr != nullptr;
+    }
     if (sc) sc->launches++;
     GM_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1414,7 +1575,19 @@ struct engine {
       if (gm_vectors_need_alt(tmp)) return 1;
       if (gm_vectors_view_get(tmp, &vv)) return 1;
     }
+    const int order = (int)prog.getOrder();
+    const bool may_push = !all && gv.push_divisor > 0 && sizeof(U) <= 16 && sizeof(E) == 4;
+    if (may_push && gv.world == 1 && order != GraphMat::ALL_EDGES) {
+      // one GPU: k_apply counts the next frontier's entries, which needs the column-major companion's c_ptr now
+      const gm_matrix_view& M0 = order == GraphMat::OUT_EDGES ? gv.AT : gv.A;
+      if (M0.nnz >= gv.push_min_nnz && !M0.c_ptr) {
+        if (gm_graph_push_ready(g, order == GraphMat::OUT_EDGES ? 1 : 0)) return 1;
+        if (gm_graph_view_get(g, &gv)) return 1;
+      }
+    }
     GM_CUDA_OK(cudaEventRecord(rg.e0, st));
+    if (may_push && is_atomic_min<P>::value && sizeof(U) == 4)  // identity of min everywhere: see k_apply<RESET>
+      GM_CUDA_OK(cudaMemsetAsync(vv.y_val, 0xff, (size_t)gv.n_local_pad * sizeof(U), st));
     if (all && set_all_active(gv, &sc)) return 1;
     int it = 0, converged = 1;
     // Fixed iteration count and no do_every_iteration hook: nothing on the host depends on the
@@ -1440,6 +1613,7 @@ struct engine {
       for (auto& e : evs) GM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDefault));
     }
     int pending = 0;
+    bool counted = false;
     void* xbuf[2] = {vv.x_val, vv.x_alt};
     int cur = 0;
     while (1) {
@@ -1481,7 +1655,7 @@ struct engine {
           cur ^= 1;
         }
       } else {
-        if (apply(prog, gv, vv, &sc, fuse)) return 1;
+        if (apply(prog, gv, vv, &sc, fuse, may_push, &counted)) return 1;
       }
       // every iteration of a run over mapped peers ends with the barrier: it orders the stores into the
       // peers' buffers before their next pass, and it ORs the "changed" flag on the device
@@ -1495,9 +1669,10 @@ struct engine {
           pending = 0;
         }
       } else {
-        GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GM_CUDA_OK(cudaMemcpyAsync(gv.h_flags, gv.d_flags, 12 * sizeof(int), cudaMemcpyDeviceToHost, st));
         GM_CUDA_OK(cudaStreamSynchronize(st));
         int changed = gv.h_flags[0];
+        sc.next_entries = counted ? (long long)*reinterpret_cast<unsigned long long*>(gv.h_flags + 10) : -1;
         if (gv.world > 1 && !peers && gm_graph_allreduce_or(g, &changed)) return 1;
         converged = !changed;
         if (timing) {

@@ -22,6 +22,7 @@ class SSSP : public GraphMat::GraphProgram<gm_sssp::distance_type, gm_sssp::dist
  public:
   typedef gm_sssp::distance_type distance_type;
   static const bool gm_reorderable = true;  // min
+  static const bool gm_atomic_min = true;   // ... of 32-bit unsigned values: sparse passes fold with atomicMin
   GM_HD SSSP() {
     this->order = GraphMat::OUT_EDGES;
     this->process_message_requires_vertexprop = false;
@@ -54,6 +55,7 @@ class DeltaStepping : public GraphMat::GraphProgram<gm_sssp::distance_type, gm_s
   int delta;
   int bid;
   static const bool gm_reorderable = true;  // min
+  static const bool gm_atomic_min = true;   // ... of 32-bit unsigned values: sparse passes fold with atomicMin
   GM_HD DeltaStepping(int d = 1) {
     delta = d;
     bid = 0;

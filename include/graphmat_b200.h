@@ -167,6 +167,8 @@ int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int siz
 int gm_vectors_destroy(gm_vectors* v);
 int gm_vectors_view_get(const gm_vectors* v, gm_vectors_view* out);
 int gm_vectors_scratch(gm_vectors* v, long long bytes, void** out);   /* device scratch, grown on demand */
+int gm_vectors_aux(gm_vectors* v, long long bytes, void** out);       /* second, persistent block, handed out filled with
+                                                                         0xff bytes (the "no winner yet" table of the atomic push) */
 
 /* ---- multi-GPU exchange (replaces the MPI sends of include/GMDP/multinode/spmspv.h:61-116 and the
  *      Allreduce of include/GraphMatRuntime.h:226).  The library calls these between send and SpMSpV /

@@ -255,8 +255,13 @@ def _sssp_run(Gs, src0):
     return Gs.get_vertexproperties()["distance"].copy(), st
 
 
+@pytest.mark.parametrize("sort_path", [False, True])
 @pytest.mark.parametrize("case", ["rmat12", "rmat14_heavy16", "random", "test_mtx"])
-def test_push_path_forced(case):
+def test_push_path_forced(case, sort_path, monkeypatch):
+    """BFS (last writer) and SSSP (min) take the atomic push; GM_NO_ATOMIC_PUSH sends them through the sorted-triples
+    path that programs without such a trait use -- both must reproduce the reference's fold"""
+    if sort_path:
+        monkeypatch.setenv("GM_NO_ATOMIC_PUSH", "1")
     t = 4
     heavy = 0
     if case == "rmat12":
@@ -368,3 +373,51 @@ def test_bad_edge_ids_are_refused():
         capi.Graph.from_edges(8, s, d, None, capi.PR_DTYPE)
     with pytest.raises(RuntimeError, match="outside"):
         capi.Graph.from_edges(8, d, np.array([0, 1, 2], np.int32), None, capi.PR_DTYPE)
+
+
+# ---- BASELINE.json's configurations at their size, against the UNMODIFIED reference (oracle/_ref) ----
+from oracle import ref  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not ref.available("bfs"), reason="oracle/_ref is built where /root/reference exists")
+REF_THREADS = 8  # the reference's OpenMP thread count fixes its vertex permutation; the engine is told the same
+
+
+@needs_ref
+@pytest.mark.parametrize("scale", [20, 22])
+def test_pagerank_rmat_vs_reference(scale):
+    """PageRank x10 on RMAT-20/22 (the rows above 100 K entries go through k_heavy_fadd32<16>): bit-identical"""
+    n, s, d, _ = ref.rmat_edges(scale, 16, seed=1)
+    rpr, rdeg, rit, _ = ref.pagerank(n, s, d, None, threads=REF_THREADS, iterations=10)
+    pr, deg, it = apps.pagerank(n, s, d, None, threads=REF_THREADS, iterations=10)
+    assert it == rit == 10 and (deg == rdeg).all()
+    assert_rel(pr, rpr)
+    assert (pr == rpr).all()
+
+
+@needs_ref
+def test_bfs_rmat22_vs_reference():
+    """BASELINE config 2: BFS on RMAT scale-22, depth AND parent arrays bit-exact (src/BFS.cpp:110-156)"""
+    n, s, d, _ = ref.rmat_edges(22, 16, seed=1)
+    src0 = int(s.min())
+    rd, rp, rit, rreach, _ = ref.bfs(n, s, d, src0, None, threads=REF_THREADS)
+    depth, parent, it, reach = apps.bfs(n, s, d, src0, threads=REF_THREADS)
+    assert it == rit and reach == rreach
+    assert (depth == rd).all() and (parent == rp).all()
+
+
+@needs_ref
+def test_sssp_rmat22_vs_reference():
+    n, s, d, w = ref.rmat_edges(22, 16, seed=1, weight_max=127, weight_seed=2)
+    src0 = int(s.min())
+    rdist, rit, rreach, _ = ref.sssp(n, s, d, w, src0, threads=REF_THREADS)
+    dist, it, reach = apps.sssp(n, s, d, w, src0, threads=REF_THREADS)
+    assert it == rit and reach == rreach and (dist == rdist).all()
+
+
+@needs_ref
+def test_deltastepping_rmat20_vs_reference():
+    n, s, d, w = ref.rmat_edges(20, 16, seed=1, weight_max=127, weight_seed=2)
+    src0 = int(s.min())
+    rdist, rbucket, rnb, rreach, _ = ref.deltastepping(n, s, d, w, 16, src0, threads=REF_THREADS)
+    dist, bucket, nb, reach = apps.deltastepping(n, s, d, w, 16, src0, threads=REF_THREADS)
+    assert nb == rnb and reach == rreach and (dist == rdist).all() and (bucket == rbucket).all()

@@ -190,8 +190,8 @@ def test_sharded_engine_peer_memory(world):
     n, s, d, v = util.rmat_numpy(12, weight_max=127)
     src0 = util.first_source(s)
     threads = 4
-    mk = lambda dt, **kw: [capi.Graph.from_edges(n, s, d, kw.pop("val", None), dt, threads=threads, rank=r, world=world,
-                                                 heavy_threshold=64, coop_threshold=512) for r in range(world)]
+    mk = lambda dt, val=None: [capi.Graph.from_edges(n, s, d, val, dt, threads=threads, rank=r, world=world,
+                                                     heavy_threshold=64, coop_threshold=512) for r in range(world)]
     # ---- PageRank: fixed iterations (async loop) and until convergence ----
     graphs = mk(capi.PR_DTYPE)
     lr = exchange.LocalRanks.with_peers(graphs, lambda g: (capi.Vectors(g, capi.PROG_DEGREE), capi.Vectors(g, capi.PROG_PAGERANK)))
