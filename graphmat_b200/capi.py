@@ -50,7 +50,8 @@ class MatrixView(C.Structure):
                 ("h_val", C.c_void_p), ("slice_ptr", C.c_void_p), ("s_col", C.c_void_p), ("s_val", C.c_void_p),
                 ("nnz", C.c_longlong), ("n_segs", C.c_int), ("seg_len", C.c_int), ("seg_ptr", C.c_void_p),
                 ("seg_row", C.c_void_p), ("c_ptr", C.c_void_p), ("c_row", C.c_void_p), ("c_rank", C.c_void_p),
-                ("c_val", C.c_void_p), ("rank_bits", C.c_int), ("n_long", C.c_int), ("long_entries", C.c_longlong)]
+                ("c_val", C.c_void_p), ("rank_bits", C.c_int), ("n_big_cols", C.c_int), ("big_cols", C.c_void_p),
+                ("n_long", C.c_int), ("long_entries", C.c_longlong)]
 
 
 class GraphView(C.Structure):
@@ -190,6 +191,17 @@ class Graph:
         o = cls._opts(threads, rank, world, heavy_threshold, order_like, build_mask, coop_threshold=coop_threshold)
         _check(lib().gm_graph_create(C.byref(h), C.c_int(n), C.c_longlong(len(src)), _p(src), _p(dst),
                                      _p(val) if val is not None else None, C.c_int(4),
+                                     C.c_int(np.dtype(vdtype).itemsize), C.byref(o)), "gm_graph_create")
+        return cls(h, vdtype)
+
+    @classmethod
+    def from_device_edges(cls, n, nnz, src_ptr, dst_ptr, val_ptr, vdtype, threads=4, rank=0, world=1, heavy_threshold=0,
+                          order_like=None, build_mask=0):
+        """edge list already in device memory (int32 arrays, public 1-based ids); the arrays are only read"""
+        h = C.c_void_p()
+        o = cls._opts(threads, rank, world, heavy_threshold, order_like, build_mask, on_device=True)
+        _check(lib().gm_graph_create(C.byref(h), C.c_int(n), C.c_longlong(nnz), C.c_void_p(src_ptr), C.c_void_p(dst_ptr),
+                                     C.c_void_p(val_ptr) if val_ptr else None, C.c_int(4),
                                      C.c_int(np.dtype(vdtype).itemsize), C.byref(o)), "gm_graph_create")
         return cls(h, vdtype)
 

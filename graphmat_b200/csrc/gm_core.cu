@@ -330,6 +330,7 @@ static void matrix_free(gm_matrix& M) {
   cudaFree(M.c_row);
   cudaFree(M.c_rank);
   cudaFree(M.c_val);
+  cudaFree(M.big_cols);
   cudaFree(M.slot_vertex);
   cudaFree(M.row_len);
   cudaFree(M.h_ptr);
@@ -514,6 +515,8 @@ static void fill_view(const gm_matrix& M, gm_matrix_view* v) {
   v->c_rank = M.c_rank;
   v->c_val = M.c_val;
   v->rank_bits = M.rank_bits;
+  v->n_big_cols = M.n_big_cols;
+  v->big_cols = M.big_cols;
   v->n_long = M.n_long;
   v->long_entries = M.long_entries;
 }
@@ -1036,6 +1039,11 @@ __global__ void k_len_slice_to_ll(const int* row_len, int first, int n, long lon
   if (i < n) out[i] = row_len[first + i];
 }
 
+__global__ void k_big_cols(const long long* c_ptr, int n_full, int thr, int* n_big, int* big_cols) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_full && c_ptr[c + 1] - c_ptr[c] > thr) big_cols[atomicAdd(n_big, 1)] = c;
+}
+
 static int build_push(gm_graph* g, gm_matrix& M) {
   if (M.push_built) return 0;
   cudaStream_t st = g->stream;
@@ -1082,6 +1090,15 @@ static int build_push(gm_graph* g, gm_matrix& M) {
   if (total > 0) k_csc_fill<<<nblk(total), 256, 0, st>>>(ks, es, row, rank, val, total, M.c_row, M.c_rank, cv, cnt);
   CK(cudaGetLastError());
   if (exclusive_scan_ll(cnt, M.c_ptr, g->n_full, st)) return 1;
+  {  // the columns above GM_PUSH_BIG_COL entries (hubs): a short list the atomic push walks with many blocks
+    int* nb = nullptr;
+    if (dalloc(&nb, 1) || dalloc(&M.big_cols, (size_t)(total / GM_PUSH_BIG_COL + 1))) return 1;
+    CK(cudaMemsetAsync(nb, 0, 4, st));
+    k_big_cols<<<nblk(g->n_full), 256, 0, st>>>(M.c_ptr, g->n_full, GM_PUSH_BIG_COL, nb, M.big_cols);
+    CK(cudaGetLastError());
+    if (d2h(&M.n_big_cols, nb, 4, st)) return 1;
+    cudaFree(nb);
+  }
   cudaFree(k0); cudaFree(k1); cudaFree(e0); cudaFree(e1); cudaFree(val); cudaFree(row); cudaFree(rank);
   cudaFree(len_ll); cudaFree(row_off); cudaFree(cnt);
   M.push_built = true;

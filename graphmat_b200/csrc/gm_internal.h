@@ -12,6 +12,7 @@
 #define GM_DEFAULT_COOP_THRESHOLD 16384
 #define GM_SEG_LEN 2048
 #define GM_DEFAULT_LONG_THRESHOLD 32768
+#define GM_PUSH_BIG_COL 2048  /* == GM_PUSH_BIG of gm_engine.cuh */
 
 void gm_set_error(const std::string& s);
 
@@ -45,6 +46,8 @@ struct gm_matrix {
   int* c_rank = nullptr;       // position of the entry in its row's fold order
   void* c_val = nullptr;       // edge value
   int rank_bits = 0;           // bits needed for c_rank
+  int n_big_cols = 0;          // columns above GM_PUSH_BIG_COL entries
+  int* big_cols = nullptr;
   int n_long = 0;              // rows longer than gm_graph::long_threshold (a prefix: rows are stored longest first)
   long long long_entries = 0;  // h_ptr[n_long]
   bool push_built = false;

@@ -101,6 +101,38 @@ def attach_peers(G, dist):
     return G.enable_peers(capi.ALLGATHER_HOST_FN(gather))
 
 
+def upload_vp(G, vp, rank):
+    """whole public-order array `vp` (identical on every rank) -> the sharded graph: each rank moves only its slice
+    over PCIe when peers are mapped, else every rank uploads the whole array and keeps what it owns"""
+    if G.peers_enabled():
+        lo, hi = G.slice_range(rank)
+        G.set_vertexproperties_slice(vp[lo:hi])
+    else:
+        G.set_vertexproperties(vp)
+
+
+def collect_vp(G, dtype, nv, dist, rank, world):
+    """the whole vertex-property array in public order, on every rank (tests / parity checks)"""
+    import numpy as np
+    import torch
+    if dist is None or world == 1:
+        return G.get_vertexproperties()
+    if G.peers_enabled():
+        mine = G.get_vertexproperties_slice(rank)
+        per = (nv + world - 1) // world
+        buf = np.zeros(per, dtype)
+        buf[:len(mine)] = mine
+        t = torch.from_numpy(buf.view(np.uint8).copy()).cuda()
+        allt = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allt, t)
+        return allt.cpu().numpy().view(dtype)[:nv]       # slice q starts at q * per: the padding lies beyond nv
+    out = np.zeros(nv, dtype)
+    G.get_vertexproperties(out)                          # owned entries; the others stay 0
+    t = torch.from_numpy(out.view(np.int32).copy()).cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)             # owners are disjoint
+    return t.cpu().numpy().view(dtype)
+
+
 class LocalRanks:
     """`world` ranks of one sharded graph inside one process / one GPU (test harness).
 

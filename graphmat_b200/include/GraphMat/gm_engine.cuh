@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <utility>
 #include <vector>
 #include <algorithm>
 
@@ -69,6 +70,15 @@ template <class P, class = void>
 struct is_atomic_min : std::false_type {};
 template <class P>
 struct is_atomic_min<P, typename std::enable_if<P::gm_atomic_min>::type> : std::true_type {};
+// `static bool gm_null_message(const T&)`: true for a message that cannot change any receiver (process_message
+// maps it to the identity of reduce_function AND apply ignores that identity) -- DeltaStepping's MAX_DIST from the
+// vertices outside the current bucket (src/DeltaStepping.cpp:79-84).  k_send then leaves the sender's x bit clear:
+// the frontier shrinks to the vertices that matter and the pass can take the sparse-frontier path.  Vertex
+// properties, "changed" flags and iteration counts are the same as with the message sent.
+template <class P, class T, class = void>
+struct has_null_message : std::false_type {};
+template <class P, class T>
+struct has_null_message<P, T, decltype(void(P::gm_null_message(std::declval<const T&>())))> : std::true_type {};
 // `static const bool gm_fadd32_exact = true;`: T = U = float, process_message is
 // res = message, reduce is a += b and messages are >= 0.  Long rows then use the
 // bit-exact parallel emulation of the serial fp32 fold (k_heavy_fadd32).
@@ -208,20 +218,27 @@ __device__ __forceinline__ X ld_gather(const X* x, int c, int hot_limit) {
 
 // -------------------------------------------------------------------- send --
 // x[i] = send_message(vp[i]) where active; x bits = active bits.
+// ybits != NULL: the same sweep clears y's bit words (Clear(&y), GraphMatRuntime.h:139) -- one launch less per iteration.
 template <class P, class T, class V>
 __global__ void __launch_bounds__(256) k_send(prog_bytes<P> pb, int n_pad, const V* __restrict__ vp,
                                               const unsigned* __restrict__ active, T* __restrict__ x,
-                                              unsigned* __restrict__ xbits) {
+                                              unsigned* __restrict__ xbits, unsigned* __restrict__ ybits) {
   const P& prog = pb.get();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   unsigned w = active[i >> 5];
-  if ((w >> (i & 31)) & 1u) {
+  bool on = (w >> (i & 31)) & 1u;
+  if (on) {
     T t;
     (void)prog.P::send_message(vp[i], t);
-    x[i] = t;
+    if constexpr (has_null_message<P, T>::value) on = !P::gm_null_message(t);
+    if (on) x[i] = t;
   }
-  if ((i & 31) == 0) xbits[i >> 5] = w;
+  if constexpr (has_null_message<P, T>::value) w = __ballot_sync(0xffffffffu, on);  // n_pad is a multiple of 32
+  if ((i & 31) == 0) {
+    xbits[i >> 5] = w;
+    if (ybits) ybits[i >> 5] = 0u;
+  }
 }
 
 // ------------------------------------------------------------------- apply --
@@ -300,6 +317,86 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
   if (!FUSE && c_ptr) {
     for (int o = 16; o; o >>= 1) ents += __shfl_down_sync(0xffffffffu, ents, o);
     if ((threadIdx.x & 31) == 0 && ents) atomicAdd(next_entries, ents);
+  }
+}
+
+// ---- ACTIVE_ONLY programs: the same two steps as sweeps over BIT WORDS ----
+// A warp loads 32 words of the active set (y bits); only the non-empty words are visited, lane j taking bit j, so
+// a step touches 32 consecutive vertices exactly like the per-vertex kernels do, but a sparse frontier costs a few
+// hundred blocks instead of one thread per vertex (BFS on RMAT-22: 13 us -> ~3 us per sweep).
+template <class P, class T, class V>
+__global__ void __launch_bounds__(256) k_send_words(prog_bytes<P> pb, int n_words, const V* __restrict__ vp,
+                                                    const unsigned* __restrict__ active, T* __restrict__ x,
+                                                    unsigned* __restrict__ xbits, unsigned* __restrict__ ybits) {
+  const P& prog = pb.get();
+  const int lane = threadIdx.x & 31;
+  const int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  const int w = w0 + lane;
+  unsigned word = w < n_words ? active[w] : 0u;
+  unsigned out = word;
+  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    lanes &= lanes - 1;
+    const unsigned m = __shfl_sync(0xffffffffu, word, src);
+    bool on = (m >> lane) & 1u;
+    if (on) {
+      const int i = (w0 + src) * 32 + lane;
+      T t;
+      (void)prog.P::send_message(vp[i], t);
+      if constexpr (has_null_message<P, T>::value) on = !P::gm_null_message(t);
+      if (on) x[i] = t;
+    }
+    if constexpr (has_null_message<P, T>::value) {
+      const unsigned kept = __ballot_sync(0xffffffffu, on);
+      if (lane == src) out = kept;
+    }
+  }
+  if (w < n_words) {
+    xbits[w] = out;
+    if (ybits) ybits[w] = 0u;
+  }
+}
+template <class P, class T, class U, class V, bool RESET>
+__global__ void __launch_bounds__(256) k_apply_words(prog_bytes<P> pb, int n_words, U* __restrict__ y,
+                                                     const unsigned* __restrict__ ybits, V* __restrict__ vp,
+                                                     unsigned* __restrict__ active, int* __restrict__ flags,
+                                                     const long long* __restrict__ c_ptr,
+                                                     unsigned long long* __restrict__ next_entries, int x_off) {
+  alignas(16) unsigned char pbuf[sizeof(P)];
+  memcpy(pbuf, pb.b, sizeof(P));
+  P& prog = *reinterpret_cast<P*>(pbuf);  // apply is non-const in the reference
+  const int lane = threadIdx.x & 31;
+  const int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  const int w = w0 + lane;
+  const unsigned word = w < n_words ? __ldg(ybits + w) : 0u;
+  unsigned out = 0u;
+  unsigned long long ents = 0;
+  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    lanes &= lanes - 1;
+    const unsigned m = __shfl_sync(0xffffffffu, word, src);
+    bool changed = false;
+    if ((m >> lane) & 1u) {
+      const int i = (w0 + src) * 32 + lane;
+      V cur = vp[i];
+      const V old = cur;
+      const U msg = y[i];
+      prog.P::apply(msg, cur);
+      changed = (old != cur);
+      vp[i] = cur;
+      if constexpr (RESET) reinterpret_cast<unsigned*>(y)[i] = 0xffffffffu;
+      if (changed && c_ptr) ents += (unsigned long long)(__ldg(c_ptr + x_off + i + 1) - __ldg(c_ptr + x_off + i));
+    }
+    const unsigned cm = __ballot_sync(0xffffffffu, changed);
+    if (lane == src) out = cm;
+  }
+  if (w < n_words) active[w] = out;  // setAllInactive + set where changed
+  if (__ballot_sync(0xffffffffu, out != 0) != 0 && lane == 0) raise_flag(flags);
+  if (c_ptr) {
+    for (int o = 16; o; o >>= 1) ents += __shfl_down_sync(0xffffffffu, ents, o);
+    if (lane == 0 && ents) atomicAdd(next_entries, ents);
   }
 }
 
@@ -1077,8 +1174,10 @@ __global__ void __launch_bounds__(128)
 //     pass 1 walks the same entries again and the one whose position won writes y[row] (and hands win[row]
 //     back as -1).  Positions are unique within a row, so exactly one entry writes: the same bits as the fold.
 // Work split: a warp takes 32 bit words of x; every active column with at most GM_PUSH_BIG entries is walked
-// by the whole warp, longer ones are queued and walked by the whole grid (k_push_atomic_big).
+// by the whole warp; the longer ones (a short list fixed at build time, gm_matrix_view::big_cols) are walked by
+// extra blocks of the same launch, all together.
 constexpr int GM_PUSH_BIG = 2048;
+constexpr int GM_PUSH_LANE = 16;
 template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
 __device__ __forceinline__ void push_entry(const P& prog, const gm_matrix_view& M, long long e, const T& xv,
                                            const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
@@ -1104,47 +1203,73 @@ __device__ __forceinline__ void push_entry(const P& prog, const gm_matrix_view& 
 }
 template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
 __global__ void __launch_bounds__(256)
-    k_push_atomic(prog_bytes<P> pb, gm_matrix_view M, int n_words, const unsigned* __restrict__ xbits,
+    k_push_atomic(prog_bytes<P> pb, gm_matrix_view M, int n_words, int word_blocks, const unsigned* __restrict__ xbits,
                   const T* __restrict__ x, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
-                  int* __restrict__ win, int* __restrict__ n_big, int* __restrict__ big_cols, int queue_big) {
+                  int* __restrict__ win) {
   const P& prog = pb.get();
+  if ((int)blockIdx.x >= word_blocks) {
+    // the blocks behind the word sweep: the (few, precomputed) columns above GM_PUSH_BIG entries, each walked
+    // by all of these blocks together when its x bit is set
+    const long long g = (blockIdx.x - word_blocks) * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (gridDim.x - word_blocks) * (long long)blockDim.x;
+    __shared__ int act[1024];
+    __shared__ int n_act;
+    for (int base = 0; base < M.n_big_cols; base += 1024) {  // every block compacts the ACTIVE big columns itself
+      if (threadIdx.x == 0) n_act = 0;
+      __syncthreads();
+      for (int k = base + threadIdx.x; k < M.n_big_cols && k < base + 1024; k += blockDim.x) {
+        const int c = __ldg(M.big_cols + k);
+        if (test_bit(xbits, c)) act[atomicAdd(&n_act, 1)] = c;
+      }
+      __syncthreads();
+      const int na = n_act;
+      for (int j = 0; j < na; j++) {
+        const int c = act[j];
+        const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
+        const T xv = x[c];
+        for (long long e = beg + g; e < end; e += stride) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int w = warp * 32 + lane;
   unsigned word = w < n_words ? __ldg(xbits + w) : 0u;
-  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  // a lane first walks the SHORT columns of its own word by itself (a sparse frontier has about one active column
+  // per word: 32 words = 32 independent chains per warp); columns above GM_PUSH_LANE entries are left for the
+  // whole warp, 32 entries per step
+  unsigned longer = 0u;
+  {
+    unsigned m = word;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int c = w * 32 + b;
+      const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
+      if (end - beg > GM_PUSH_LANE) {
+        if (end - beg <= GM_PUSH_BIG) longer |= 1u << b;
+        continue;
+      }
+      if (beg == end) continue;
+      const T xv = x[c];
+      for (long long e = beg; e < end; e++) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
+    }
+  }
+  unsigned lanes = __ballot_sync(0xffffffffu, longer != 0);
   while (lanes) {
     const int src = __ffs(lanes) - 1;
     lanes &= lanes - 1;
-    unsigned m = __shfl_sync(0xffffffffu, word, src);
+    unsigned m = __shfl_sync(0xffffffffu, longer, src);
     const int cbase = (warp * 32 + src) * 32;
     while (m) {
       const int c = cbase + __ffs(m) - 1;
       m &= m - 1;
       const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
-      if (end - beg > GM_PUSH_BIG) {
-        if (queue_big && lane == 0) big_cols[atomicAdd(n_big, 1)] = c;
-        continue;
-      }
-      if (beg == end) continue;
       const T xv = x[c];
       for (long long e = beg + lane; e < end; e += 32) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
     }
-  }
-}
-template <class P, class T, class U, class V, class E, bool NEEDVP, bool IDENT, int MODE>
-__global__ void __launch_bounds__(256)
-    k_push_atomic_big(prog_bytes<P> pb, gm_matrix_view M, const int* __restrict__ n_big, const int* __restrict__ big_cols,
-                      const T* __restrict__ x, const V* __restrict__ vp, U* __restrict__ y, unsigned* __restrict__ ybits,
-                      int* __restrict__ win) {
-  const P& prog = pb.get();
-  const int nb = *n_big;
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = gridDim.x * (long long)blockDim.x;
-  for (int k = 0; k < nb; k++) {
-    const int c = big_cols[k];
-    const long long beg = __ldg(M.c_ptr + c), end = __ldg(M.c_ptr + c + 1);
-    const T xv = x[c];
-    for (long long e = beg + g; e < end; e += stride) push_entry<P, T, U, V, E, NEEDVP, IDENT, MODE>(prog, M, e, xv, vp, y, ybits, win);
   }
 }
 
@@ -1165,6 +1290,8 @@ struct step_counters {
   long long push_passes = 0;
   long long last_frontier_cols = -1, last_frontier_entries = -1;  // of the latest sparse pass (trace only)
   long long next_entries = -1;  // entries of the coming pass's frontier when k_apply counted them (-1: unknown)
+  bool ybits_clean = false;     // k_send already cleared y's bit words for the coming pass
+  bool counted_by_kernel = false;  // gm_push_count ran in this iteration (its scratch words overlap k_apply's counter)
 };
 
 template <class P>
@@ -1193,8 +1320,15 @@ struct engine {
     const int n = gv.n_local_pad;
     T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
     unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
-    k_send<P, T, V><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), n, (const V*)gv.vertexproperty, gv.active_bits, xloc, xb);
-    if (sc) sc->launches++;
+    if (prog.getActivity() != GraphMat::ALL_VERTICES) {
+      const int nw = n >> 5;
+      k_send_words<P, T, V><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(pack(prog), nw, (const V*)gv.vertexproperty, gv.active_bits,
+                                                                      xloc, xb, sc ? vv.y_bits : nullptr);
+    } else {
+      k_send<P, T, V><<<(n + 255) / 256, 256, 0, st>>>(pack(prog), n, (const V*)gv.vertexproperty, gv.active_bits, xloc, xb,
+                                                       sc ? vv.y_bits : nullptr);
+    }
+    if (sc) { sc->launches++; sc->ybits_clean = true; }
     GM_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -1298,6 +1432,7 @@ struct engine {
         long long n_ent = sc ? sc->next_entries : -1;  // counted by the previous k_apply (one GPU)
         if (n_ent < 0 || !M.c_ptr) {
           if (gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+          if (sc) sc->counted_by_kernel = true;
         }
         if (sc) { sc->last_frontier_cols = n_act; sc->last_frontier_entries = n_ent; }
         if (n_ent * push_div <= M.nnz) {
@@ -1314,26 +1449,19 @@ struct engine {
           if constexpr (!ACCUM && (LASTW || AMIN)) sorted_path = getenv("GM_NO_ATOMIC_PUSH") != nullptr;  // tests
           if constexpr (!ACCUM && (LASTW || AMIN)) if (!sorted_path) {
             // no sort, no host round trip: atomicMin into y, or "largest fold position wins" in two sweeps
-            void *aux = nullptr, *scratch = nullptr;
+            void* aux = nullptr;
             if (LASTW && gm_vectors_aux(vecs, (long long)MP.n_slots * 4, &aux)) return 1;
-            if (gm_vectors_scratch(vecs, (MP.nnz / GM_PUSH_BIG + 2) * 4, &scratch)) return 1;
             int* win = (int*)aux;
-            int* big_cols = (int*)scratch;
-            int* n_big = gv.d_flags + 13;
-            GM_CUDA_OK(cudaMemsetAsync(n_big, 0, sizeof(int), st));
             const int n_words = gv.n_full >> 5;
-            const unsigned blocks = (unsigned)(((n_words + 31) / 32 + 7) / 8);
-            const unsigned bigb = (unsigned)gm_sm_count() * 4;
+            const int wblocks = ((n_words + 31) / 32 + 7) / 8;
+            const unsigned blocks = (unsigned)(wblocks + (MP.n_big_cols > 0 ? gm_sm_count() * 4 : 0));
             if constexpr (LASTW) {
-              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 0><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, win, n_big, big_cols, 1);
-              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 0><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, win);
-              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 1><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, win, n_big, big_cols, 0);
-              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 1><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, win);
-              if (sc) sc->launches += 4;
-            } else {
-              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 2><<<blocks, 256, 0, st>>>(pb, MP, n_words, vv.x_bits, x, vp, y, vv.y_bits, nullptr, n_big, big_cols, 1);
-              k_push_atomic_big<P, T, U, V, E, NEEDVP, IDENT, 2><<<bigb, 256, 0, st>>>(pb, MP, n_big, big_cols, x, vp, y, vv.y_bits, nullptr);
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 0><<<blocks, 256, 0, st>>>(pb, MP, n_words, wblocks, vv.x_bits, x, vp, y, vv.y_bits, win);
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 1><<<blocks, 256, 0, st>>>(pb, MP, n_words, wblocks, vv.x_bits, x, vp, y, vv.y_bits, win);
               if (sc) sc->launches += 2;
+            } else {
+              k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 2><<<blocks, 256, 0, st>>>(pb, MP, n_words, wblocks, vv.x_bits, x, vp, y, vv.y_bits, nullptr);
+              if (sc) sc->launches += 1;
             }
             if (sc) { sc->edges += n_ent; sc->push_passes++; }
             GM_CUDA_OK(cudaGetLastError());
@@ -1341,7 +1469,10 @@ struct engine {
           }
           if (sorted_path) {
             // any other reduce_function: (row, fold position, value) triples, radix-sorted, folded in the reference's order
-            if (n_act < 0 && gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+            if (n_act < 0) {
+              if (gm_push_count(gv.owner, which, vecs, &n_act, &n_ent)) return 1;
+              if (sc) sc->counted_by_kernel = true;
+            }
             if (n_ent == 0) {
               if (sc) sc->push_passes++;
               return 0;
@@ -1458,7 +1589,9 @@ struct engine {
                     gm_vectors* vecs, const EP* ep = nullptr) {
     cudaStream_t st = (cudaStream_t)gv.stream;
     const int order = (int)prog.getOrder();
-    if (!ep) GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
+    if (!ep && !(sc && sc->ybits_clean))
+      GM_CUDA_OK(cudaMemsetAsync(vv.y_bits, 0, (size_t)(gv.n_local_pad >> 5) * 4, st));  // Clear(&y)
+    if (sc) sc->ybits_clean = false;
     if (order == GraphMat::OUT_EDGES) return mult(prog, gv, gv.AT, vv, allact, false, sc, vecs, ep);
     if (order == GraphMat::IN_EDGES) return mult(prog, gv, gv.A, vv, allact, false, sc, vecs, ep);
     if (order == GraphMat::ALL_EDGES) {
@@ -1497,10 +1630,17 @@ struct engine {
       if (count_next && gv.world == 1 && order != GraphMat::ALL_EDGES)
         c_ptr = order == GraphMat::OUT_EDGES ? gv.AT.c_ptr : gv.A.c_ptr;
       unsigned long long* next = reinterpret_cast<unsigned long long*>(gv.d_flags + 10);
-      if (c_ptr) GM_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-      k_apply<P, T, U, V, false, RESET><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (U*)vv.y_val, vv.y_bits,
-                                                                        (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb,
-                                                                        c_ptr, next, gv.rank * n);
+      if (c_ptr && (!sc || sc->counted_by_kernel)) GM_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+      if (sc) sc->counted_by_kernel = false;
+      if (prog.getActivity() != GraphMat::ALL_VERTICES) {
+        const int nw = n >> 5;
+        k_apply_words<P, T, U, V, RESET><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(
+            pack(prog), nw, (U*)vv.y_val, vv.y_bits, (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, c_ptr, next, gv.rank * n);
+      } else {
+        k_apply<P, T, U, V, false, RESET><<<apply_blocks(n), 256, 0, st>>>(pack(prog), gv.n_local, n, (U*)vv.y_val, vv.y_bits,
+                                                                          (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, xloc, xb,
+                                                                          c_ptr, next, gv.rank * n);
+      }
       if (counted) *counted = c_ptr != nullptr;
     }
     if (sc) sc->launches++;
@@ -1617,7 +1757,7 @@ struct engine {
     void* xbuf[2] = {vv.x_val, vv.x_alt};
     int cur = 0;
     while (1) {
-      GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, sizeof(int), st));
+      GM_CUDA_OK(cudaMemsetAsync(gv.d_flags, 0, 12 * sizeof(int), st));  // [0] changed, [8..11] frontier counters
       gm_vectors_view vc = vv;  // this iteration's message vector
       vc.x_val = xbuf[cur];
       EP ep;

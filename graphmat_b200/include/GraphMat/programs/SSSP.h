@@ -67,6 +67,9 @@ class DeltaStepping : public GraphMat::GraphProgram<gm_sssp::distance_type, gm_s
                              distance_type& res) const {
     res = (message < gm_sssp::kMaxDist) ? (message + edge_val) : gm_sssp::kMaxDist;
   }
+  // a vertex outside the current bucket sends MAX_DIST, which process_message hands on as MAX_DIST and apply
+  // ignores (distance > MAX_DIST is never true): the engine may drop such messages (gm_engine.cuh, has_null_message)
+  static GM_HD bool gm_null_message(const distance_type& m) { return m == gm_sssp::kMaxDist; }
   GM_HD bool send_message(const DeltaSteppingDS& vertex, distance_type& message) const {
     message = (vertex.bucket == bid) ? vertex.distance : gm_sssp::kMaxDist;
     return true;

@@ -72,6 +72,8 @@ typedef struct gm_matrix_view {
   const int* c_rank;            /* position of the entry in its row's fold order (ascending native column) */
   const void* c_val;            /* edge value per entry */
   int rank_bits;                /* c_rank < 2^rank_bits */
+  int n_big_cols;               /* x indices whose column holds more than 2048 entries (walked by many blocks) */
+  const int* big_cols;
   /* the n_long longest rows (more than long_threshold entries) hold long_entries entries, [0, long_entries) of
    * h_col: fp32-sum programs gather these into a staging buffer with the whole GPU before one block folds them */
   int n_long;

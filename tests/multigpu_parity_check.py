@@ -51,28 +51,10 @@ def main():
             exchange.attach(G, None, dist)
 
     def collect(G, dtype, nv):
-        """the whole vertex-property array in public order, on every rank"""
-        if G.peers_enabled():
-            mine = G.get_vertexproperties_slice(rank)
-            per = (nv + world - 1) // world
-            buf = np.zeros(per, dtype)
-            buf[:len(mine)] = mine
-            t = torch.from_numpy(buf.view(np.uint8).copy()).cuda()
-            allt = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(allt, t)
-            return allt.cpu().numpy().view(dtype)[:nv]    # slice q starts at q * per: the padding lies beyond nv
-        out = np.zeros(nv, dtype)
-        G.get_vertexproperties(out)                       # owned entries; the others stay 0
-        t = torch.from_numpy(out.view(np.int32).copy()).cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)          # owners are disjoint
-        return t.cpu().numpy().view(dtype)
+        return exchange.collect_vp(G, dtype, nv, dist, rank, world)
 
     def upload(G, vp):
-        if G.peers_enabled():
-            lo, hi = G.slice_range(rank)
-            G.set_vertexproperties_slice(vp[lo:hi])
-        else:
-            G.set_vertexproperties(vp)
+        exchange.upload_vp(G, vp, rank)
 
     def report(what, same):
         nonlocal ok
