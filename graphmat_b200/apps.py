@@ -129,3 +129,37 @@ def sgd(m, n, src, dst, val, K=20, iterations=10, lam=0.001, step=0.00000035, th
     after = rmse()
     out = G.get_vertexproperties()
     return out["lv"].copy(), before, after
+
+
+def incremental_pagerank(n, src, dst, val=None, threads=4, iterations=-1, **kw):
+    """src/IncrementalPageRank.cpp:128-175 -> (pagerank f64[n], delta f64[n], degree i32[n], iterations)"""
+    G = gm.Graph.from_edges(n, src, dst, val, gm.DPR_DTYPE, threads=threads, **kw)
+    init = np.zeros(1, gm.DPR_DTYPE)
+    init["delta"], init["pagerank"], init["degree"] = 0.3, 0.3, 0   # dPR(), :39-43
+    G.set_all_vertexproperty(init[0])
+    G.set_all_active()
+    G.run(gm.PROG_DEGREE_DPR, None, 1)
+    G.set_all_active()
+    state = gm.DeltaPageRankState(0.3, 0)
+    st = G.run(gm.PROG_DELTAPAGERANK, state, iterations if iterations > 0 else gm.UNTIL_CONVERGENCE)
+    vp = G.get_vertexproperties()
+    return vp["pagerank"].copy(), vp["delta"].copy(), vp["degree"].copy(), st.iterations
+
+
+def topsort(n, src, dst, val=None, threads=4, **kw):
+    """src/TopologicalSort.cpp:141-190 -> (order u32[n], in_degree i32[n], iterations, unreachable)"""
+    G = gm.Graph.from_edges(n, src, dst, val, gm.TOPSORT_DTYPE, threads=threads, **kw)
+    init = np.zeros(1, gm.TOPSORT_DTYPE)
+    init["topsort_order"], init["in_degree"] = 0xFFFFFFFF, 0        # Vertex_type(), :44-47
+    G.set_all_vertexproperty(init[0])
+    G.run(gm.PROG_INDEGREE, None, 1)                                 # ALL_VERTICES: no setAllActive in the app (:153)
+    vp = G.get_vertexproperties()
+    roots = np.nonzero(vp["in_degree"] == 0)[0]                      # :156-167
+    vp["topsort_order"][roots] = 0
+    G.set_vertexproperties(vp)
+    G.set_all_inactive()
+    G.set_active_many(roots + 1)
+    st = G.run(gm.PROG_TOPSORT, gm.TopSortState(1), gm.UNTIL_CONVERGENCE)
+    unreachable = G.nvertices - int(G.reduce(gm.REDUCE_REACHABLE))   # :132-138, 177-178
+    out = G.get_vertexproperties()
+    return out["topsort_order"].copy(), out["in_degree"].copy(), st.iterations, unreachable

@@ -19,6 +19,7 @@ OUT_EDGES, IN_EDGES, ALL_EDGES = 0, 1, 2
 UNTIL_CONVERGENCE = -1
 PROG_DEGREE, PROG_PAGERANK, PROG_BFS, PROG_SSSP, PROG_DELTASTEPPING = 1, 2, 3, 4, 5
 PROG_SGD20, PROG_RMSE20, PROG_SGD32, PROG_RMSE32, PROG_SGD4, PROG_RMSE4 = 6, 7, 8, 9, 10, 11
+PROG_DEGREE_DPR, PROG_DELTAPAGERANK, PROG_INDEGREE, PROG_TOPSORT = 12, 13, 14, 15
 REDUCE_REACHABLE, REDUCE_BUCKET_NOT_EMPTY, REDUCE_SQERR = 1, 2, 3
 SGD_PROGRAMS = {20: (PROG_SGD20, PROG_RMSE20), 32: (PROG_SGD32, PROG_RMSE32), 4: (PROG_SGD4, PROG_RMSE4)}
 
@@ -27,6 +28,8 @@ PR_DTYPE = np.dtype([("pagerank", np.float32), ("degree", np.int32)])
 BFS_DTYPE = np.dtype([("depth", np.uint32), ("parent", np.uint64), ("id", np.uint64)], align=True)
 SSSP_DTYPE = np.dtype([("distance", np.uint32)])
 DS_DTYPE = np.dtype([("distance", np.uint32), ("bucket", np.int32)])
+DPR_DTYPE = np.dtype([("delta", np.float64), ("pagerank", np.float64), ("degree", np.int32)], align=True)
+TOPSORT_DTYPE = np.dtype([("topsort_order", np.uint32), ("in_degree", np.int32)])
 
 
 def latent_dtype(K):
@@ -93,6 +96,14 @@ class DeltaSteppingState(C.Structure):
     _fields_ = [("delta", C.c_int), ("bid", C.c_int)]
 
 
+class DeltaPageRankState(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("iter", C.c_int)]
+
+
+class TopSortState(C.Structure):
+    _fields_ = [("current_topsort_order", C.c_uint)]
+
+
 class SGDState(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("step", C.c_double)]
 
@@ -115,7 +126,7 @@ SYMBOLS = [
     "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts", "gm_abi_struct_sizes",
     "gm_graph_exchange_buffer", "gm_graph_enable_peers", "gm_graph_peers_enabled", "gm_graph_peer_barrier",
     "gm_graph_push_x", "gm_vectors_need_alt", "gm_graph_slice_begin", "gm_graph_set_vertexproperties_slice",
-    "gm_graph_get_vertexproperties_slice", "gm_vectors_aux",
+    "gm_graph_get_vertexproperties_slice", "gm_vectors_aux", "gm_graph_set_active_array",
 ]
 
 
@@ -249,6 +260,12 @@ class Graph:
 
     def set_active(self, v):
         _check(lib().gm_graph_set_active(self.h, C.c_int(v)), "gm_graph_set_active")
+
+    def set_active_many(self, ids):
+        """the active set = exactly these public ids"""
+        flags = np.zeros(self.nvertices, np.uint8)
+        flags[np.asarray(ids, dtype=np.int64) - 1] = 1
+        _check(lib().gm_graph_set_active_array(self.h, _p(flags)), "gm_graph_set_active_array")
 
     def set_inactive(self, v):
         _check(lib().gm_graph_set_inactive(self.h, C.c_int(v)), "gm_graph_set_inactive")

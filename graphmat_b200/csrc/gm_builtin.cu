@@ -7,6 +7,8 @@
 
 #include "GraphMat/gm_engine.cuh"
 #include "GraphMat/programs/BFS.h"
+#include "GraphMat/programs/IncrementalPageRank.h"
+#include "GraphMat/programs/TopologicalSort.h"
 #include "GraphMat/programs/PageRank.h"
 #include "GraphMat/programs/SGD.h"
 #include "GraphMat/programs/SSSP.h"
@@ -56,6 +58,29 @@ template <unsigned K> struct binder<RMSEProgram<K> > {
   static int bytes() { return 0; }
   static void in(RMSEProgram<K>&, const void*) {}
   static void out(const RMSEProgram<K>&, void*) {}
+};
+
+template <> struct binder<Degree<dPR, int> > {
+  static int bytes() { return 0; }
+  static void in(Degree<dPR, int>&, const void*) {}
+  static void out(const Degree<dPR, int>&, void*) {}
+};
+template <> struct binder<DeltaPageRank> {
+  static int bytes() { return sizeof(gm_deltapagerank_state); }
+  static void in(DeltaPageRank& p, const void* s) {
+    if (s) { p.alpha = ((const gm_deltapagerank_state*)s)->alpha; p.iter = ((const gm_deltapagerank_state*)s)->iter; }
+  }
+  static void out(const DeltaPageRank& p, void* s) { if (s) ((gm_deltapagerank_state*)s)->iter = p.iter; }
+};
+template <> struct binder<InDegree<TopSortVertex, int> > {
+  static int bytes() { return 0; }
+  static void in(InDegree<TopSortVertex, int>&, const void*) {}
+  static void out(const InDegree<TopSortVertex, int>&, void*) {}
+};
+template <> struct binder<TopSort> {
+  static int bytes() { return sizeof(gm_topsort_state); }
+  static void in(TopSort& p, const void* s) { if (s) p.current_topsort_order = ((const gm_topsort_state*)s)->current_topsort_order; }
+  static void out(const TopSort& p, void* s) { if (s) ((gm_topsort_state*)s)->current_topsort_order = p.current_topsort_order; }
 };
 
 enum { OP_RUN, OP_SEND, OP_SPMSPV, OP_APPLY, OP_SIZES };
@@ -122,6 +147,10 @@ int route(int program, const call& c) {
     case GM_PROG_RMSE32: return dispatch<RMSEProgram<32> >(c);
     case GM_PROG_SGD4: return dispatch<SGDProgram<4> >(c);
     case GM_PROG_RMSE4: return dispatch<RMSEProgram<4> >(c);
+    case GM_PROG_DEGREE_DPR: return dispatch<Degree<dPR, int> >(c);
+    case GM_PROG_DELTAPAGERANK: return dispatch<DeltaPageRank>(c);
+    case GM_PROG_INDEGREE: return dispatch<InDegree<TopSortVertex, int> >(c);
+    case GM_PROG_TOPSORT: return dispatch<TopSort>(c);
   }
   gm_set_error("unknown program id");
   return 1;

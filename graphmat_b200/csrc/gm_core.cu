@@ -813,6 +813,7 @@ extern "C" int gm_graph_synchronize(const gm_graph* g) {
   return 0;
 }
 
+static int staging(gm_graph* g, size_t bytes);
 // ----------------------------------------------------------------- activity --
 __global__ void k_fill_words(unsigned* bits, int n_valid, int n_pad, unsigned fill) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -864,6 +865,27 @@ static int set_active(gm_graph* g, int v, int on) {
   if (owner != g->rank) return 0;
   k_set_bit<<<1, 1, 0, g->stream>>>(g->active, local, on);
   CK(cudaGetLastError());
+  return 0;
+}
+__global__ void k_set_active_array(unsigned* bits, const unsigned char* flags, int n, int npart, const int* xidx, int n_pad,
+                                   int rank) {
+  int pub = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pub >= n || !flags[pub]) return;
+  int xi = xidx[to_native0(pub + 1, n, npart)];
+  if (xi / n_pad != rank) return;
+  int local = xi % n_pad;
+  atomicOr(bits + (local >> 5), 1u << (local & 31));
+}
+// the active set from a host array of n flags in public-id order (flags[v-1] != 0 <=> setActive(v), all others inactive):
+// what the apps' "for every vertex: if (...) G.setActive(i)" loops amount to (src/TopologicalSort.cpp:157-167)
+extern "C" int gm_graph_set_active_array(gm_graph* g, const unsigned char* flags) {
+  if (staging(g, (size_t)g->n)) return 1;
+  CK(cudaMemcpyAsync(g->staging, flags, (size_t)g->n, cudaMemcpyHostToDevice, g->stream));
+  CK(cudaMemsetAsync(g->active, 0, (size_t)(g->n_pad >> 5) * 4, g->stream));
+  k_set_active_array<<<nblk(g->n), 256, 0, g->stream>>>(g->active, (const unsigned char*)g->staging, g->n, g->ref_threads * 16,
+                                                       g->d_xidx, g->n_pad, g->rank);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g->stream));
   return 0;
 }
 extern "C" int gm_graph_set_active(gm_graph* g, int v) { return set_active(g, v, 1); }
@@ -1244,8 +1266,8 @@ extern "C" int gm_push_sort(gm_graph* g, gm_push_plan* plan) {
 // ------------------------------------------------------------------ vectors --
 extern "C" int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof_T, int sizeof_U) {
   *out = nullptr;
-  if (sizeof_T <= 0 || sizeof_T % 4 || sizeof_U <= 0) {
-    gm_set_error("gm_vectors_create: sizeof_T must be a positive multiple of 4");
+  if (sizeof_T <= 0 || sizeof_U <= 0) {
+    gm_set_error("gm_vectors_create: message sizes must be positive");
     return 1;
   }
   gm_vectors* v = new gm_vectors();

@@ -87,8 +87,10 @@ __global__ void k_peer_barrier(ptr_table flags, int rank, int world, unsigned ro
 
 // ---- slice of x -> every peer -------------------------------------------------------------------
 // words: the slice as 4-byte words, wp per vertex; dense: every vertex, else only where the bit is set
+// W: unsigned (messages that are a multiple of 4 bytes) or unsigned char (e.g. TopSort's bool)
+template <class W>
 __global__ void __launch_bounds__(256)
-    k_push_x(ptr_table val, ptr_table bits, int n_peers, const unsigned* __restrict__ lval,
+    k_push_x(ptr_table val, ptr_table bits, int n_peers, const W* __restrict__ lval,
              const unsigned* __restrict__ lbits, long long word_off, int bit_off, int n_pad, int wp, int dense) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)n_pad * wp;
@@ -99,8 +101,8 @@ __global__ void __launch_bounds__(256)
   if (t >= total) return;
   const int i = (int)(t / wp);
   if (!dense && !((lbits[bit_off + (i >> 5)] >> (i & 31)) & 1u)) return;
-  const unsigned v = lval[word_off + t];
-  for (int q = 0; q < n_peers; q++) reinterpret_cast<unsigned*>(val.p[q])[word_off + t] = v;
+  const W v = lval[word_off + t];
+  for (int q = 0; q < n_peers; q++) reinterpret_cast<W*>(val.p[q])[word_off + t] = v;
 }
 
 __host__ __device__ inline int to_native0(int pub1, int n, int npart) {
@@ -168,8 +170,13 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
   mine.pid = (long long)getpid();
   mine.ptr = (unsigned long long)out->local;
   cudaGetDevice(&mine.device);
-  mine.ok = cudaIpcGetMemHandle(&mine.handle, out->local) == cudaSuccess ? 1 : 0;
-  cudaGetLastError();
+  std::string why;
+  {
+    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, out->local);
+    mine.ok = e == cudaSuccess ? 1 : 0;
+    if (e != cudaSuccess) why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+  }
   std::vector<peer_blob> all(g->world);
   if (g->host_gather(g->host_ctx, &mine, all.data(), (int)sizeof(peer_blob))) {
     gm_set_error("peer memory: the host all-gather callback failed");
@@ -186,11 +193,18 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
         cudaGetLastError();
       }
       out->peer[q] = (void*)all[q].ptr;
-    } else if (!all[q].ok || cudaIpcOpenMemHandle(&out->peer[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError();
+    } else if (!all[q].ok) {
+      if (why.empty()) why = "the peer could not export its buffer (cudaIpcGetMemHandle failed there)";
       bad = 1;
     } else {
-      out->opened[q] = true;
+      cudaError_t e = cudaIpcOpenMemHandle(&out->peer[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        bad = 1;
+      } else {
+        out->opened[q] = true;
+      }
     }
   }
   // agree on the outcome: a rank that could not map a peer must not leave the others storing into it
@@ -205,7 +219,7 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
     host_barrier(g);
     cudaFree(out->local);
     *out = gm_sym();
-    gm_set_error("peer memory: a peer buffer could not be mapped (no P2P / IPC between these devices)");
+    gm_set_error("peer memory: a peer buffer could not be mapped (" + (why.empty() ? std::string("another rank failed") : why) + ")");
     return 1;
   }
   return 0;
@@ -303,11 +317,19 @@ extern "C" int gm_graph_push_x(gm_graph* g, gm_vectors* v, int dense) {
       pb.p[np] = v->s_bits.peer[q];
       np++;
     }
-  const int wp = v->sizeof_T / 4;
-  const long long total = (long long)g->n_pad * wp;
-  k_push_x<<<nblk(total), 256, 0, g->stream>>>(pv, pb, np, (const unsigned*)v->x_val, v->x_bits,
-                                               (long long)g->rank * g->n_pad * wp, g->rank * (g->n_pad >> 5), g->n_pad, wp,
-                                               dense);
+  if (v->sizeof_T % 4 == 0) {
+    const int wp = v->sizeof_T / 4;
+    const long long total = (long long)g->n_pad * wp;
+    k_push_x<unsigned><<<nblk(total), 256, 0, g->stream>>>(pv, pb, np, (const unsigned*)v->x_val, v->x_bits,
+                                                           (long long)g->rank * g->n_pad * wp, g->rank * (g->n_pad >> 5),
+                                                           g->n_pad, wp, dense);
+  } else {
+    const int wp = v->sizeof_T;
+    const long long total = (long long)g->n_pad * wp;
+    k_push_x<unsigned char><<<nblk(total), 256, 0, g->stream>>>(pv, pb, np, (const unsigned char*)v->x_val, v->x_bits,
+                                                                (long long)g->rank * g->n_pad * wp, g->rank * (g->n_pad >> 5),
+                                                                g->n_pad, wp, dense);
+  }
   CK(cudaGetLastError());
   return 0;
 }

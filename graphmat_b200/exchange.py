@@ -92,7 +92,8 @@ def attach_peers(G, dist):
             if on_gpu:
                 src, out = src.cuda(), out.cuda()
             dist.all_gather_into_tensor(out, src)
-            C.memmove(all_, out.cpu().numpy().ctypes.data, world * nbytes)
+            host = out.cpu().numpy()  # keep the array alive while its bytes are copied out
+            C.memmove(all_, host.ctypes.data, world * nbytes)
             return 0
         except Exception as e:
             print("graphmat_b200.exchange: host all-gather failed:", e)

@@ -154,6 +154,7 @@ int gm_graph_set_all_active(gm_graph* g);
 int gm_graph_set_all_inactive(gm_graph* g);
 int gm_graph_set_active(gm_graph* g, int v);
 int gm_graph_set_inactive(gm_graph* g, int v);
+int gm_graph_set_active_array(gm_graph* g, const unsigned char* flags); /* n flags, public-id order (host): the whole active set */
 /* include/Graph.h:300-364; values are sizeof_V bytes each, arrays are in public-id order (index v-1) */
 int gm_graph_set_all_vertexproperty(gm_graph* g, const void* value);
 int gm_graph_set_vertexproperty(gm_graph* g, int v, const void* value);
@@ -249,8 +250,15 @@ enum {
   GM_PROG_SGD32 = 8,
   GM_PROG_RMSE32 = 9,
   GM_PROG_SGD4 = 10,
-  GM_PROG_RMSE4 = 11
+  GM_PROG_RMSE4 = 11,
+  /* the remaining POD vertex programs */
+  GM_PROG_DEGREE_DPR = 12,     /* src/IncrementalPageRank.cpp:53-78  V = dPR              */
+  GM_PROG_DELTAPAGERANK = 13,  /* src/IncrementalPageRank.cpp:80-123 V = dPR              */
+  GM_PROG_INDEGREE = 14,       /* src/TopologicalSort.cpp:60-87      V = Vertex_type      */
+  GM_PROG_TOPSORT = 15         /* src/TopologicalSort.cpp:90-130     V = Vertex_type      */
 };
+typedef struct gm_deltapagerank_state { double alpha; int iter; } gm_deltapagerank_state; /* src/IncrementalPageRank.cpp:82-83 */
+typedef struct gm_topsort_state { unsigned int current_topsort_order; } gm_topsort_state;   /* src/TopologicalSort.cpp:93 */
 typedef struct gm_pagerank_state { float alpha; } gm_pagerank_state;                  /* src/PageRank.cpp:84 */
 typedef struct gm_bfs_state { unsigned int current_depth; } gm_bfs_state;             /* src/BFS.cpp:64 */
 typedef struct gm_deltastepping_state { int delta, bid; } gm_deltastepping_state;     /* src/DeltaStepping.cpp:67-68 */
@@ -264,6 +272,7 @@ int gm_step_spmspv(gm_graph* g, int program, const void* state, gm_vectors* tmp)
 int gm_step_apply(gm_graph* g, int program, void* state, gm_vectors* tmp, int* changed);
 
 /* Graph::applyReduceAllVertices (include/Graph.h:377-381) for the app drivers' three map functions */
+/* GM_REDUCE_REACHABLE also serves src/TopologicalSort.cpp:132-138 ("unreachable" = nvertices - reachable) */
 enum { GM_REDUCE_REACHABLE = 1,      /* src/BFS.cpp:101-108 etc.: count of vertices whose first uint field < UINT_MAX */
        GM_REDUCE_BUCKET_NOT_EMPTY = 2, /* src/DeltaStepping.cpp:109-111, param = bid */
        GM_REDUCE_SQERR = 3 };        /* src/SGD.cpp:158-161: sum of the trailing double (sqerr) */

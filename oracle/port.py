@@ -86,6 +86,27 @@ def sgd(m, n, src, dst, val, K=20, iterations=10, lam=0.001, step=0.00000035, th
     return lv, rmse[0], rmse[1]
 
 
+def incremental_pagerank(n, src, dst, val=None, threads=4, iterations=-1):
+    """src/IncrementalPageRank.cpp:128-175 -> (pagerank f64[n], delta f64[n], degree i32[n], iterations)"""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    pr, de, deg = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.int32)
+    it = lib().gmo_incremental_pagerank(C.c_int(threads), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst), _p(val),
+                                        C.c_int(iterations), _p(pr), _p(de), _p(deg))
+    return pr, de, deg, it
+
+
+def topsort(n, src, dst, val=None, threads=4):
+    """src/TopologicalSort.cpp:141-190 -> (order u32[n], in_degree i32[n], iterations, unreachable)"""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    order, indeg = np.empty(n, np.uint32), np.empty(n, np.int32)
+    un = C.c_int()
+    it = lib().gmo_topsort(C.c_int(threads), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst), _p(val), _p(order), _p(indeg),
+                           C.byref(un))
+    return order, indeg, it, un.value
+
+
 def rowblock_sum_f32(n, src, dst, row_begin, row_end, x, xbit, y, ybit, threads=4):
     src, dst = _i32(src), _i32(dst)
     lib().gmo_rowblock_sum_f32(C.c_int(threads), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst), C.c_int(row_begin),

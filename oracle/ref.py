@@ -133,6 +133,29 @@ def sgd(m, n, src, dst, val, K=20, iterations=10, lam=0.001, step=0.00000035, th
     return lv, rmse[0], rmse[1], ms.value
 
 
+def incremental_pagerank(n, src, dst, val=None, threads=4, iterations=-1):
+    """-> (pagerank f64[n], delta f64[n], degree i32[n], iterations, ms)."""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    pr, de, deg = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.int32)
+    ms = C.c_double()
+    it = _lib("incrementalpagerank").gm_ref_incremental_pagerank(
+        C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst), _p(val), C.c_int(iterations),
+        _p(pr), _p(de), _p(deg), C.byref(ms))
+    return pr, de, deg, it, ms.value
+
+
+def topsort(n, src, dst, val=None, threads=4):
+    """-> (order u32[n], in_degree i32[n], iterations, unreachable, ms)."""
+    src, dst = _i32(src), _i32(dst)
+    val = _i32(val) if val is not None else np.ones(len(src), np.int32)
+    order, indeg = np.empty(n, np.uint32), np.empty(n, np.int32)
+    un, ms = C.c_int(), C.c_double()
+    it = _lib("topologicalsort").gm_ref_topsort(C.c_int(threads), C.c_int(n), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst),
+                                                _p(val), _p(order), _p(indeg), C.byref(un), C.byref(ms))
+    return order, indeg, it, un.value, ms.value
+
+
 class PageRankSession:
     """Build once, time run_graph_program per call (bench.py reference arm / cpu_baseline)."""
 

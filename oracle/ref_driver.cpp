@@ -32,6 +32,10 @@
 #include "src/DeltaStepping.cpp"
 #elif defined(GM_REF_APP_SGD)
 #include "src/SGD.cpp"
+#elif defined(GM_REF_APP_INCREMENTALPAGERANK)
+#include "src/IncrementalPageRank.cpp"
+#elif defined(GM_REF_APP_TOPOLOGICALSORT)
+#include "src/TopologicalSort.cpp"
 #else
 #error "pick one reference app"
 #endif
@@ -303,6 +307,75 @@ int gm_ref_deltastepping(int threads, int m, int n, int nnz, const int* src, con
     if (bucket) bucket[i - 1] = p.bucket;
   }
   return deltastep.bid;
+}
+#endif
+
+#if defined(GM_REF_APP_INCREMENTALPAGERANK)
+// run_pagerank, /root/reference/src/IncrementalPageRank.cpp:128-175.  iterations <= 0: UNTIL_CONVERGENCE.
+int gm_ref_incremental_pagerank(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val,
+                                int iterations, double* pagerank, double* delta, int* degree, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<dPR> G;
+  DeltaPageRank dpr;
+  Degree<dPR, int> dg;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  auto dg_tmp = GraphMat::graph_program_init(dg, G);
+  G.setAllActive();
+  GraphMat::run_graph_program(&dg, G, 1, &dg_tmp);
+  GraphMat::graph_program_clear(dg_tmp);
+  auto dpr_tmp = GraphMat::graph_program_init(dpr, G);
+  double t0 = now_ms();
+  G.setAllActive();
+  GraphMat::run_graph_program(&dpr, G, iterations > 0 ? iterations : GraphMat::UNTIL_CONVERGENCE, &dpr_tmp);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(dpr_tmp);
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    dPR p = G.getVertexproperty(i);
+    pagerank[i - 1] = p.pagerank;
+    delta[i - 1] = p.delta;
+    degree[i - 1] = p.degree;
+  }
+  return dpr.iter;
+}
+#endif
+
+#if defined(GM_REF_APP_TOPOLOGICALSORT)
+// run_topsort, /root/reference/src/TopologicalSort.cpp:141-190.  Returns TopSort's iteration count.
+int gm_ref_topsort(int threads, int m, int n, int nnz, const int* src, const int* dst, const int* val,
+                   unsigned int* order, int* in_degree, int* unreachable_out, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  GraphMat::Graph<Vertex_type> G;
+  ingest(G, m, n, nnz, src, dst, val, true);
+  InDegree<Vertex_type> indeg;
+  TopSort topsort;
+  auto d_tmp = GraphMat::graph_program_init(indeg, G);
+  auto b_tmp = GraphMat::graph_program_init(topsort, G);
+  double t0 = now_ms();
+  GraphMat::run_graph_program(&indeg, G, 1, &d_tmp);
+  G.setAllInactive();
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    auto v = G.getVertexproperty(i);
+    if (v.in_degree == 0) {
+      G.setActive(i);
+      v.topsort_order = 0;
+      G.setVertexproperty(i, v);
+    }
+  }
+  GraphMat::run_graph_program(&topsort, G, GraphMat::UNTIL_CONVERGENCE, &b_tmp);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(d_tmp);
+  GraphMat::graph_program_clear(b_tmp);
+  int un = 0;
+  G.applyReduceAllVertices(&un, unreachable);
+  if (unreachable_out) *unreachable_out = un;
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    Vertex_type p = G.getVertexproperty(i);
+    order[i - 1] = p.topsort_order;
+    in_degree[i - 1] = p.in_degree;
+  }
+  return (int)topsort.current_topsort_order - 1;
 }
 #endif
 

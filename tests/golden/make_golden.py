@@ -70,6 +70,22 @@ def main():
     for K in (20, 32):
         lv, r0, r1, _ = ref.sgd(300, 360, u, it_, r_, K=K, threads=4)
         save("ratings_k%d_t4" % K, threads=4, lv=lv, rmse0=r0, rmse1=r1)
+    # --- IncrementalPageRank and TopologicalSort (RMAT-12; a seeded DAG; the reference's fixture) ---
+    for t in (1, 4):
+        n, s, d, _ = util.rmat_numpy(12)
+        dpr, ddelta, ddeg, dit, _ = ref.incremental_pagerank(n, s, d, None, threads=t)
+        dpr5, ddelta5, _, _, _ = ref.incremental_pagerank(n, s, d, None, threads=t, iterations=5)
+        order, indeg, tit, unreach, _ = ref.topsort(n, s, d, None, threads=t)
+        nd, ds_, dd_ = util.random_dag(3000, 40000, seed=1)
+        dorder, dindeg, dtit, dun, _ = ref.topsort(nd, ds_, dd_, None, threads=t)
+        m = util.TEST_MTX
+        mpr, mdelta, mdeg, mit, _ = ref.incremental_pagerank(m["n"], m["src"], m["dst"], m["val"], threads=t)
+        morder, mindeg, mtit, mun, _ = ref.topsort(m["n"], m["src"], m["dst"], m["val"], threads=t)
+        save("f3_t%d" % t, threads=t, dpr_pagerank=dpr, dpr_delta=ddelta, dpr_degree=ddeg, dpr_iterations=dit,
+             dpr_pagerank5=dpr5, dpr_delta5=ddelta5, ts_order=order, ts_in_degree=indeg, ts_iterations=tit,
+             ts_unreachable=unreach, dag_order=dorder, dag_in_degree=dindeg, dag_iterations=dtit, dag_unreachable=dun,
+             mtx_dpr_pagerank=mpr, mtx_dpr_delta=mdelta, mtx_dpr_degree=mdeg, mtx_dpr_iterations=mit,
+             mtx_ts_order=morder, mtx_ts_in_degree=mindeg, mtx_ts_iterations=mtit, mtx_ts_unreachable=mun)
 
 
 if __name__ == "__main__":

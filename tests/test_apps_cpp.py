@@ -110,3 +110,25 @@ def test_custom_program_cpp(policy, threads):
     env = {"default": {}, "always_push": {"GM_PUSH_DIVISOR": "1", "GM_PUSH_MIN_NNZ": "0"},
            "never_push": {"GM_PUSH_DIVISOR": "0"}}[policy]
     assert "custom program ok" in run("CustomProgramCheck", 6, threads=threads, extra_env=env)
+
+
+def test_f3_apps_on_fixtures(tmp_path):
+    """IncrementalPageRank and TopologicalSort through the C++ mirror"""
+    g = np.load(os.path.join(util.GOLDEN, "f3_t4.npz"))
+    m = util.TEST_MTX
+    prefix = str(tmp_path / "test.bin.mtx")
+    write_mtx(prefix, m["n"], m["n"], m["src"], m["dst"], m["val"])
+    d = str(tmp_path / "dump.txt")
+    out = run("IncrementalPageRank", prefix, "--dump", d)
+    assert "Completed %d iterations" % int(g["mtx_dpr_iterations"]) in out
+    a = np.loadtxt(d)
+    assert (a[:, 1] == g["mtx_dpr_degree"]).all() and (a[:, 2] == g["mtx_dpr_pagerank"]).all()
+    out = run("TopologicalSort", prefix, "--dump", d)
+    a = np.loadtxt(d, dtype=np.int64)
+    assert (a[:, 1] == g["mtx_ts_order"]).all() and (a[:, 2] == g["mtx_ts_in_degree"]).all()
+    nd, s, dd = util.random_dag(3000, 40000, seed=1)
+    prefix = str(tmp_path / "dag.bin.mtx")
+    write_mtx(prefix, nd, nd, s, dd, np.ones(len(s), np.int32))
+    out = run("TopologicalSort", prefix, "--dump", d)
+    a = np.loadtxt(d, dtype=np.int64)
+    assert (a[:, 1] == g["dag_order"]).all() and "Top Sort order 1 :" in out

@@ -421,3 +421,46 @@ def test_deltastepping_rmat20_vs_reference():
     rdist, rbucket, rnb, rreach, _ = ref.deltastepping(n, s, d, w, 16, src0, threads=REF_THREADS)
     dist, bucket, nb, reach = apps.deltastepping(n, s, d, w, 16, src0, threads=REF_THREADS)
     assert nb == rnb and reach == rreach and (dist == rdist).all() and (bucket == rbucket).all()
+
+
+# ---- IncrementalPageRank (ACTIVE_ONLY, fp64, order-sensitive sum) and TopologicalSort (T = bool) ----
+@pytest.mark.parametrize("t", [1, 4])
+@pytest.mark.parametrize("heavy", [0, 16])
+def test_golden_f3_programs_gpu(t, heavy):
+    g = load("f3_t%d" % t)
+    n, s, d, _ = util.rmat_numpy(12)
+    kw = dict(threads=t, heavy_threshold=heavy)
+    pr, delta, deg, it = apps.incremental_pagerank(n, s, d, None, **kw)
+    assert it == int(g["dpr_iterations"]) and (deg == g["dpr_degree"]).all()
+    assert_rel(pr, g["dpr_pagerank"])
+    assert (pr == g["dpr_pagerank"]).all() and (delta == g["dpr_delta"]).all()      # every row folded in the reference's order
+    pr5, delta5, _, _ = apps.incremental_pagerank(n, s, d, None, iterations=5, **kw)
+    assert (pr5 == g["dpr_pagerank5"]).all() and (delta5 == g["dpr_delta5"]).all()
+    order, indeg, tit, un = apps.topsort(n, s, d, None, **kw)
+    assert (order == g["ts_order"]).all() and (indeg == g["ts_in_degree"]).all()
+    assert tit == int(g["ts_iterations"]) and un == int(g["ts_unreachable"])
+    nd, ds_, dd_ = util.random_dag(3000, 40000, seed=1)
+    order, indeg, tit, un = apps.topsort(nd, ds_, dd_, None, **kw)
+    assert (order == g["dag_order"]).all() and (indeg == g["dag_in_degree"]).all()
+    assert tit == int(g["dag_iterations"]) and un == 0
+    m = util.TEST_MTX
+    pr, delta, deg, it = apps.incremental_pagerank(m["n"], m["src"], m["dst"], m["val"], threads=t)
+    assert (pr == g["mtx_dpr_pagerank"]).all() and it == int(g["mtx_dpr_iterations"])
+    order, indeg, tit, un = apps.topsort(m["n"], m["src"], m["dst"], m["val"], threads=t)
+    assert (order == g["mtx_ts_order"]).all() and tit == int(g["mtx_ts_iterations"]) and un == int(g["mtx_ts_unreachable"])
+
+
+@needs_ref
+def test_f3_programs_rmat18_vs_reference(monkeypatch):
+    """larger inputs, sparse-frontier passes included (IncrementalPageRank takes the sorted-triples path: its fp64
+    sum has no trait), against the unmodified reference"""
+    n, s, d, _ = ref.rmat_edges(18, 16, seed=1)
+    rpr, rdelta, rdeg, rit, _ = ref.incremental_pagerank(n, s, d, None, threads=REF_THREADS)
+    pr, delta, deg, it = apps.incremental_pagerank(n, s, d, None, threads=REF_THREADS)
+    assert it == rit and (deg == rdeg).all()
+    assert_rel(pr, rpr)
+    assert (pr == rpr).all() and (delta == rdelta).all()
+    nd, ds_, dd_ = util.random_dag(1 << 18, 4 << 18, seed=3)
+    rorder, rindeg, rtit, run_, _ = ref.topsort(nd, ds_, dd_, None, threads=REF_THREADS)
+    order, indeg, tit, un = apps.topsort(nd, ds_, dd_, None, threads=REF_THREADS)
+    assert tit == rtit and un == run_ and (order == rorder).all() and (indeg == rindeg).all()

@@ -175,3 +175,43 @@ def test_empty_and_isolated():
     assert it == 1 and (deg == 0).all() and np.allclose(pr, 0.3)
     depth, parent, bit, reach = port.bfs(40, np.array([2], np.int32), np.array([3], np.int32), 1, threads=1)
     assert reach == 1 and bit == 1 and depth[0] == 0
+
+
+# ---- IncrementalPageRank and TopologicalSort ----
+@pytest.mark.parametrize("t", [1, 4])
+def test_golden_f3_programs(t):
+    g = load("f3_t%d" % t)
+    n, s, d, _ = util.rmat_numpy(12)
+    pr, delta, deg, it = port.incremental_pagerank(n, s, d, None, threads=t)
+    assert it == int(g["dpr_iterations"]) and (deg == g["dpr_degree"]).all()
+    assert (pr == g["dpr_pagerank"]).all() and (delta == g["dpr_delta"]).all()      # fp64, same fold order: same bits
+    pr5, delta5, _, _ = port.incremental_pagerank(n, s, d, None, threads=t, iterations=5)
+    assert (pr5 == g["dpr_pagerank5"]).all() and (delta5 == g["dpr_delta5"]).all()
+    order, indeg, tit, un = port.topsort(n, s, d, None, threads=t)
+    assert (order == g["ts_order"]).all() and (indeg == g["ts_in_degree"]).all()
+    assert tit == int(g["ts_iterations"]) and un == int(g["ts_unreachable"])
+    nd, ds_, dd_ = util.random_dag(3000, 40000, seed=1)
+    order, indeg, tit, un = port.topsort(nd, ds_, dd_, None, threads=t)
+    assert (order == g["dag_order"]).all() and (indeg == g["dag_in_degree"]).all()
+    assert tit == int(g["dag_iterations"]) and un == int(g["dag_unreachable"]) == 0
+    m = util.TEST_MTX
+    pr, delta, deg, it = port.incremental_pagerank(m["n"], m["src"], m["dst"], m["val"], threads=t)
+    assert (pr == g["mtx_dpr_pagerank"]).all() and it == int(g["mtx_dpr_iterations"])
+    order, indeg, tit, un = port.topsort(m["n"], m["src"], m["dst"], m["val"], threads=t)
+    assert (order == g["mtx_ts_order"]).all() and tit == int(g["mtx_ts_iterations"]) and un == int(g["mtx_ts_unreachable"])
+
+
+def test_topsort_is_a_topological_order():
+    """property: on a DAG every edge goes from a lower to a strictly higher level"""
+    nd, s, d = util.random_dag(2000, 30000, seed=7)
+    order, indeg, _, un = port.topsort(nd, s, d, None, threads=2)
+    assert un == 0 and (indeg == 0).all()
+    assert (order[s - 1] < order[d - 1]).all()
+
+
+def test_oracle_generator_is_the_products_generator():
+    """oracle/librmat.so (bench.py's reference arm, the -m gpu parity tests) restates the product's RMAT generator"""
+    from graphmat_b200 import capi
+    a = ref.rmat_edges(14, 16, seed=1, weight_max=127, weight_seed=2)
+    b = capi.rmat_edges(14, 16, seed=1, weight_max=127, weight_seed=2)
+    assert a[0] == b[0] and all((x == y).all() for x, y in zip(a[1:], b[1:]))

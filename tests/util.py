@@ -76,3 +76,12 @@ def ratings(n_users, n_items, nnz, seed=3):
     it = rng.choice(n_items, nnz, p=p) + 1 + n_users
     r = rng.integers(1, 6, nnz)
     return u.astype(np.int32), it.astype(np.int32), r.astype(np.int32)
+
+
+def random_dag(n, m, seed=1):
+    """seeded DAG: edges u -> v with u < v (public 1-based ids), duplicates kept"""
+    rng = np.random.default_rng(seed)
+    u = rng.integers(1, n, m)
+    v = rng.integers(1, n + 1, m)
+    keep = u < v
+    return n, u[keep].astype(np.int32), v[keep].astype(np.int32)
