@@ -63,7 +63,8 @@ class GraphView(C.Structure):
                 ("sizeof_E", C.c_int), ("nnz", C.c_longlong), ("vertexproperty", C.c_void_p),
                 ("active_bits", C.c_void_p), ("A", MatrixView), ("AT", MatrixView), ("d_flags", C.c_void_p),
                 ("h_flags", C.c_void_p), ("stream", C.c_void_p), ("aux_stream", C.c_void_p), ("ev_fork", C.c_void_p),
-                ("ev_join", C.c_void_p), ("hot_limit", C.c_int), ("owner", C.c_void_p),
+                ("ev_join", C.c_void_p), ("aux_stream2", C.c_void_p), ("aux_stream3", C.c_void_p), ("ev_join2", C.c_void_p),
+                ("ev_join3", C.c_void_p), ("hot_limit", C.c_int), ("owner", C.c_void_p),
                 ("push_divisor", C.c_int), ("push_min_nnz", C.c_longlong)]
 
 

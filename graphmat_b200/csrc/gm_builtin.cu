@@ -255,7 +255,7 @@ __global__ void k_iota(int* p, long long n) {
   if (i < n) p[i] = (int)i;
 }
 
-// one row holding a[0..n): warps = 1 -> warp-per-row kernel, 16 -> block-per-row kernel; offset shifts the
+// one row holding a[0..n): warps = 1 -> warp-per-row kernel, 16 -> block-per-row kernel, 32 -> TMA-streamed kernel; offset shifts the
 // row start inside the index array (exercises the aligned-group masking)
 extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, int offset, float* out) {
   typedef PageRank<int> P;
@@ -265,9 +265,9 @@ extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, 
   long long* dptr = nullptr;
   unsigned* dbits = nullptr;
   long long tot = n + offset;
-  cudaMalloc(&dx, tot * 4); cudaMalloc(&dcol, (tot + 16) * 4); cudaMalloc(&dval, (tot + 16) * 4);
+  cudaMalloc(&dx, (tot + 2 * gm::GM_TMA_ROUND) * 4); cudaMalloc(&dcol, (tot + 16) * 4); cudaMalloc(&dval, (tot + 16) * 4);
   cudaMalloc(&dptr, 16); cudaMalloc(&dy, 4 * 32); cudaMalloc(&dbits, 4);
-  cudaMemset(dx, 0, tot * 4);
+  cudaMemset(dx, 0, (tot + 2 * gm::GM_TMA_ROUND) * 4);
   cudaMemcpy(dx + offset, a, n * 4, cudaMemcpyHostToDevice);
   cudaMemset(dval, 0, (tot + 16) * 4);
   k_iota<<<(unsigned)((tot + 16 + 255) / 256), 256>>>(dcol, tot + 16);
@@ -280,7 +280,11 @@ extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, 
   M.n_slots = 32; M.n_heavy = 1; M.identity = 1; M.h_ptr = dptr; M.h_col = dcol; M.h_val = dval;
   P prog;
   gm::prog_bytes<P> pb = gm::pack(prog);
-  if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
+  if (warps == 32) {  // the TMA-streamed fold of the staged longest rows: dx is its own staging array
+    auto kt = gm::k_heavy_fadd32_tma<P, float, PR, true, false>;
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * gm::GM_TMA_ROUND * 4);
+    kt<<<1, gm::GM_TMA_W * 32, 2 * gm::GM_TMA_ROUND * 4>>>(pb, M, 0, 1, dx, dy, dbits, gm::epilogue<float, PR>());
+  } else if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
   else gm::k_heavy_fadd32<P, float, PR, int, true, true, 16><<<1, 512>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
   cudaError_t e = cudaDeviceSynchronize();
   unsigned bits = 0;

@@ -597,7 +597,22 @@ static int graph_common_alloc(gm_graph* g) {
   if (const char* e = getenv("GM_HOT_LIMIT")) g->hot_limit = atoi(e);
   if (const char* e = getenv("GM_PUSH_DIVISOR")) g->push_divisor = atoi(e);
   if (const char* e = getenv("GM_PUSH_MIN_NNZ")) g->push_min_nnz = atoll(e);
-  if (getenv("GM_NO_AUX_STREAM")) { cudaStreamDestroy(g->aux_stream); g->aux_stream = nullptr; }
+  CK(cudaStreamCreateWithFlags(&g->aux_stream2, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g->aux_stream3, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&g->ev_join2, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g->ev_join3, cudaEventDisableTiming));
+  {
+    // One auxiliary stream by default.  Two or three (warp-per-row heavy rows / the narrow tail on streams of
+    // their own) measured no faster (rank 0 of 8: 0.875 vs 0.812 ms per pass, 1 GPU: 3.78 vs 3.78) and, with the
+    // fused epilogue, NOT bit-identical from the second iteration on (profiles/r2_multistream_rejected.txt):
+    // kept behind GM_AUX_STREAMS for experiments only.
+    int n_aux = 1;
+    if (const char* e = getenv("GM_AUX_STREAMS")) n_aux = atoi(e);
+    if (getenv("GM_NO_AUX_STREAM")) n_aux = 0;
+    if (n_aux < 3) { cudaStreamDestroy(g->aux_stream3); g->aux_stream3 = nullptr; }
+    if (n_aux < 2) { cudaStreamDestroy(g->aux_stream2); g->aux_stream2 = nullptr; }
+    if (n_aux < 1) { cudaStreamDestroy(g->aux_stream); g->aux_stream = nullptr; }
+  }
   CK(cudaMallocHost((void**)&g->h_flags, 64));
   memset(g->h_flags, 0, 64);
   CK(cudaStreamSynchronize(st));
@@ -687,6 +702,8 @@ extern "C" int gm_graph_set_edge_values(gm_graph* g, long long nnz, const int* s
   cudaStream_t st = g->stream;
   CK(cudaStreamSynchronize(st));
   if (g->aux_stream) CK(cudaStreamSynchronize(g->aux_stream));
+  if (g->aux_stream2) CK(cudaStreamSynchronize(g->aux_stream2));
+  if (g->aux_stream3) CK(cudaStreamSynchronize(g->aux_stream3));
   const bool hasA = g->A.n_slots > 0, hasAT = g->AT.n_slots > 0;
   const bool identA = g->A.identity != 0, identAT = g->AT.identity != 0;
   int *d_src = nullptr, *d_dst = nullptr, *d_val = nullptr;
@@ -773,8 +790,12 @@ extern "C" int gm_graph_destroy(gm_graph* g) {
   gm_sym_free(g, &g->sync);
   for (void* p : g->retired) cudaFree(p);
   if (g->aux_stream) cudaStreamDestroy(g->aux_stream);
+  if (g->aux_stream2) cudaStreamDestroy(g->aux_stream2);
+  if (g->aux_stream3) cudaStreamDestroy(g->aux_stream3);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->ev_join2) cudaEventDestroy(g->ev_join2);
+  if (g->ev_join3) cudaEventDestroy(g->ev_join3);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return 0;
@@ -801,6 +822,10 @@ extern "C" int gm_graph_view_get(const gm_graph* g, gm_graph_view* v) {
   v->aux_stream = (void*)g->aux_stream;
   v->ev_fork = (void*)g->ev_fork;
   v->ev_join = (void*)g->ev_join;
+  v->aux_stream2 = (void*)g->aux_stream2;
+  v->aux_stream3 = (void*)g->aux_stream3;
+  v->ev_join2 = (void*)g->ev_join2;
+  v->ev_join3 = (void*)g->ev_join3;
   v->hot_limit = g->hot_limit;
   v->owner = const_cast<gm_graph*>(g);
   v->push_divisor = g->push_divisor;

@@ -70,8 +70,8 @@ struct gm_graph {
   int* h_flags = nullptr;
   void* staging = nullptr;
   size_t staging_bytes = 0;
-  cudaStream_t stream = nullptr, aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream = nullptr, aux_stream = nullptr, aux_stream2 = nullptr, aux_stream3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
   int hot_limit = -1;
   int long_threshold = GM_DEFAULT_LONG_THRESHOLD;
   void* push_scratch = nullptr;  // triples + sort buffers of the sparse-frontier path, grown geometrically

@@ -841,8 +841,7 @@ __global__ void __launch_bounds__(128)
 // The few rows above gm_matrix_view::n_long entries are the critical path of a pass (one block walks the row
 // round by round, each round an index load, then a gather, then the scan): their gathers are hoisted out of
 // the block.  k_stage_rows lets the whole GPU write x[h_col[k]] for those rows into a dense staging array;
-// k_heavy_fadd32<..., STAGED> then folds from that array: one coalesced 32-byte load per lane and round, the
-// same addends in the same order.
+// k_heavy_fadd32_tma (below) then folds from that array, the same addends in the same order.
 template <class T>
 __global__ void __launch_bounds__(256)
     k_stage_rows(const int* __restrict__ h_col, long long n_entries, const T* __restrict__ x, int hot_limit,
@@ -859,12 +858,11 @@ __global__ void __launch_bounds__(256)
   for (int j = 0; j < 8; j++) staged[i0 + j] = v[j];
 }
 
-template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W, bool STAGED = false, bool EPI = false>
+template <class P, class T, class V, class E, bool ALLACT, bool IDENT, int W, bool EPI = false>
 __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
     k_heavy_fadd32(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, int hot_limit,
                    const T* __restrict__ x, const unsigned* __restrict__ xbits, float* __restrict__ y,
-                   unsigned* __restrict__ ybits, const T* __restrict__ staged = nullptr,
-                   epilogue<T, V> ep = epilogue<T, V>()) {
+                   unsigned* __restrict__ ybits, epilogue<T, V> ep = epilogue<T, V>()) {
   const P& prog = pb.get();
   constexpr int WPB = (W == 1) ? 4 : W;  // warps per block
   __shared__ float sm_s;
@@ -894,27 +892,16 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
       if (i0 < end && i0 + 8 > beg) {
         int c[8];
         E ev[8];
-        if constexpr (!STAGED) {
-          *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
-          *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
-        }
+        *reinterpret_cast<int4*>(&c[0]) = ld_stream4(cols + i0);
+        *reinterpret_cast<int4*>(&c[4]) = ld_stream4(cols + i0 + 4);
 #pragma unroll
         for (int j = 0; j < 8; j++) ev[j] = ld_stream(vals + i0 + j);
         T xv[8];
-        if constexpr (STAGED) {
-          static_assert(sizeof(T) == 4, "staged rows hold 4-byte messages");
-          *reinterpret_cast<int4*>(&xv[0]) = __ldg(reinterpret_cast<const int4*>(staged + i0));
-          *reinterpret_cast<int4*>(&xv[4]) = __ldg(reinterpret_cast<const int4*>(staged + i0 + 4));
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            if ((i0 + j >= beg) && (i0 + j < end)) vmask |= 1u << j;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            bool on = (i0 + j >= beg) && (i0 + j < end);
-            if (on && !ALLACT) on = test_bit(xbits, c[j]);
-            if (on) { xv[j] = ld_gather(x, c[j], hot_limit); vmask |= 1u << j; }
-          }
+        for (int j = 0; j < 8; j++) {
+          bool on = (i0 + j >= beg) && (i0 + j < end);
+          if (on && !ALLACT) on = test_bit(xbits, c[j]);
+          if (on) { xv[j] = ld_gather(x, c[j], hot_limit); vmask |= 1u << j; }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -1006,6 +993,189 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
         atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
       }
       __syncthreads();
+    }
+  }
+}
+
+// ---------- SpMSpV: the longest rows, exact fp32 fold from the staging array through TMA --
+// The rows above gm_matrix_view::n_long entries are the critical path of a sharded pass: one block walks a row
+// round by round.  Their gathers are already hoisted out (k_stage_rows); this kernel streams the dense staging
+// array with BULK ASYNC COPIES (cp.async.bulk, the TMA engine) into a double-buffered shared-memory ring, one
+// mbarrier per buffer, so the copy of round r+1 runs under the fold of round r and a round costs shared-memory
+// reads instead of an L2 round trip.  A round is GM_TMA_ROUND = 32 warps x 2 chunks x 256 addends; every warp
+// scans its chunks under the binade of the block's entry value and hands ONE composed map to the block-level
+// scan, so the three block barriers of the protocol are paid once per 16 K addends (8 K before).  Same addends,
+// same order, same exactness argument as k_heavy_fadd32 (all q >= 0: the exit value decides).
+constexpr int GM_TMA_W = 32;                                   // warps per block
+constexpr int GM_TMA_CH = 2;                                   // 256-addend chunks per warp and round
+constexpr int GM_TMA_ROUND = GM_TMA_W * 256 * GM_TMA_CH;       // addends per round (16384 -> 64 KB per buffer)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class P, class T, class V, bool IDENT, bool EPI>
+__global__ void __launch_bounds__(GM_TMA_W * 32)
+    k_heavy_fadd32_tma(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const float* __restrict__ staged,
+                       float* __restrict__ y, unsigned* __restrict__ ybits, epilogue<T, V> ep) {
+  static_assert(sizeof(T) == 4, "staged rows hold 4-byte messages");
+  constexpr int W = GM_TMA_W, CH = GM_TMA_CH;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  float* ring = reinterpret_cast<float*>(tma_smem);  // 2 buffers of GM_TMA_ROUND floats
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ float sm_s;
+  __shared__ int sm_have, sm_fail;
+  __shared__ unsigned sm_d0[W], sm_d1[W], sm_bad[W];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase[2] = {0u, 0u};
+  for (int slot = row_begin + blockIdx.x; slot < row_end; slot += gridDim.x) {
+    const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
+    const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
+    if (threadIdx.x == 0) { sm_s = 0.f; sm_have = 0; }
+    const long long k_first = beg & ~7ll;  // 32-byte aligned start: the staging array is 256-byte aligned
+    const long long n_rounds = (end - k_first + GM_TMA_ROUND - 1) / GM_TMA_ROUND;
+    // everybody is done reading the ring (previous row) before the async proxy overwrites it
+    __syncthreads();
+    if (threadIdx.x == 0 && n_rounds > 0) {
+      mbar_expect_tx(&bar[0], GM_TMA_ROUND * 4);
+      tma_load_1d(ring, staged + k_first, GM_TMA_ROUND * 4, &bar[0]);
+    }
+    for (long long r = 0; r < n_rounds; r++) {
+      const int cur = (int)(r & 1);
+      const long long k0 = k_first + r * GM_TMA_ROUND;
+      if (threadIdx.x == 0 && r + 1 < n_rounds) {  // buffer cur^1 was released by the barrier that ended round r-1
+        mbar_expect_tx(&bar[cur ^ 1], GM_TMA_ROUND * 4);
+        tma_load_1d(ring + (cur ^ 1) * GM_TMA_ROUND, staged + k0 + GM_TMA_ROUND, GM_TMA_ROUND * 4, &bar[cur ^ 1]);
+      }
+      mbar_wait(&bar[cur], phase[cur]);
+      phase[cur] ^= 1u;
+      const float* buf = ring + cur * GM_TMA_ROUND;
+      // chunk c of warp w: addends [k0 + (w*CH + c)*256 + lane*8, +8)
+      auto load = [&](int c, float (&v)[8], unsigned& vmask) {
+        const int off = (w * CH + c) * 256 + lane * 8;
+        const float4 a = *reinterpret_cast<const float4*>(buf + off);
+        const float4 b = *reinterpret_cast<const float4*>(buf + off + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        vmask = 0;
+        const long long i0 = k0 + off;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (i0 + j >= beg && i0 + j < end) vmask |= 1u << j;
+          else v[j] = 0.f;  // outside the row: +0, the identity of the fold
+        }
+      };
+      const long long span = end - k0;
+      int nw = (int)((span + 256 * CH - 1) / (256 * CH));  // warps of this round that hold at least one addend
+      if (nw > W) nw = W;
+      int first = 0;  // warps [first, nw) are still to be applied
+      while (first < nw) {
+        const float s = sm_s;
+        const bool have = sm_have != 0;
+        fx::binade b;
+        const bool hot = have && fx::binade_of(s, b);  // block-uniform
+        if (!hot) {
+          // no usable accumulator yet: warp `first` folds its chunks alone (exact for any input)
+          if (w == first) {
+            float sq = s;
+            bool hq = have;
+            for (int c = 0; c < CH; c++) {
+              float v[8];
+              unsigned vmask;
+              load(c, v, vmask);
+              fx::warp_fold(v, vmask, sq, hq, lane);
+            }
+            if (lane == 0) { sm_s = sq; sm_have = hq ? 1 : 0; }
+          }
+          first++;
+          __syncthreads();
+          continue;
+        }
+        if (w >= first && w < nw) {
+          bool bad = false;
+          fx::qmap wt = fx::identity();
+#pragma unroll
+          for (int c = 0; c < CH; c++) {
+            float v[8];
+            unsigned vmask;
+            load(c, v, vmask);
+            fx::qmap mine = fx::identity();
+#pragma unroll
+            for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
+            const fx::qmap incl = fx::warp_scan(mine, lane);
+            fx::qmap tot;
+            tot.d0 = __shfl_sync(0xffffffffu, incl.d0, 31);
+            tot.d1 = __shfl_sync(0xffffffffu, incl.d1, 31);
+            wt = fx::compose(wt, tot);
+          }
+          const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+          if (lane == 31) { sm_d0[w] = wt.d0; sm_d1[w] = wt.d1; sm_bad[w] = anybad; }
+        }
+        __syncthreads();
+        if (w == 0) {
+          fx::qmap t = fx::identity();
+          bool bd = false;
+          if (lane >= first && lane < nw) { t.d0 = sm_d0[lane]; t.d1 = sm_d1[lane]; bd = sm_bad[lane] != 0; }
+          t = fx::warp_scan(t, lane);
+          const unsigned m_after = fx::apply(t, b.m);
+          const bool over = (lane >= first && lane < nw) && (bd || m_after >= (1u << 24));
+          const unsigned fail = __ballot_sync(0xffffffffu, over);
+          unsigned m_prev = __shfl_up_sync(0xffffffffu, m_after, 1);
+          if (lane == 0) m_prev = b.m;
+          if (fail == 0) {
+            if (lane == nw - 1) { sm_s = __fmul_rn(__uint2float_rn(m_after), b.u); sm_fail = -1; }
+          } else {
+            const int f = __ffs(fail) - 1;
+            if (lane == f) { sm_s = __fmul_rn(__uint2float_rn(m_prev), b.u); sm_fail = f; }
+          }
+        }
+        __syncthreads();
+        const int f = sm_fail;
+        if (f < 0) break;
+        if (w == f) {  // the warp whose exit would leave the binade: exact warp-level fold from its exact entry value
+          float sq = sm_s;
+          bool hq = true;
+          for (int c = 0; c < CH; c++) {
+            float v[8];
+            unsigned vmask;
+            load(c, v, vmask);
+            fx::warp_fold(v, vmask, sq, hq, lane);
+          }
+          if (lane == 0) sm_s = sq;
+        }
+        first = f + 1;
+        __syncthreads();
+      }
+      __syncthreads();  // round done: its buffer may be refilled, sm_s is final for the round
+    }
+    if constexpr (EPI) {
+      if (threadIdx.x == 0) {
+        const float res = sm_s;
+        if (fused_apply_send<P, T, float, V>(pb, ep, vtx, sm_have != 0, res)) raise_flag(ep.flag);
+      }
+    } else if (threadIdx.x == 0 && sm_have) {
+      y[vtx] = sm_s;
+      atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
     }
   }
 }
@@ -1337,26 +1507,35 @@ struct engine {
   // [n_coop, n_heavy) one warp per row.  Associative programs: two-phase segmented fold.
   // Anything else: one warp per row, batches folded serially (exact for any reduce_function).
   // EPI: the kernel that finishes a row also applies and sends (fused_apply_send); y is not written.
+  // hs[0]: the latency-bound chains (staged long rows, block-per-row), hs[1]: the warp-per-row kernel -- on separate
+  // streams when the graph has them, so that their blocks fill the SMs together with the sliced-ELL kernels
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool EPI>
   static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, int hot, const T* x, const unsigned* xbits,
-                        const V* vp, U* y, unsigned* ybits, cudaStream_t st, step_counters* sc, gm_vectors* vecs,
+                        const V* vp, U* y, unsigned* ybits, cudaStream_t const (&hs)[2], step_counters* sc, gm_vectors* vecs,
                         const EP& ep) {
     constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
+    cudaStream_t st = hs[0];
     if constexpr (FADD) {
       const int n_coop = M.n_coop;
       int coop_begin = 0;
       if constexpr (ALLACT && sizeof(T) == 4) {
-        // the longest rows: gathers by the whole GPU into a staging array, then one block per row folds from it
+        // the longest rows: gathers by the whole GPU into a staging array, then one block per row folds from it,
+        // streaming the array through TMA into shared memory (k_heavy_fadd32_tma)
         static const bool no_stage = getenv("GM_NO_STAGE") != nullptr;
         if (M.n_long > 0 && !no_stage) {
           void* scratch = nullptr;
-          if (gm_vectors_scratch(vecs, (M.long_entries + 64) * (long long)sizeof(T), &scratch)) return 1;
+          if (gm_vectors_scratch(vecs, (M.long_entries + 64 + 2 * GM_TMA_ROUND) * (long long)sizeof(T), &scratch)) return 1;
           T* staged = (T*)scratch;
           const long long groups = (M.long_entries + 7) / 8;
           k_stage_rows<T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(M.h_col, M.long_entries, x, hot, staged);
-          // 32 warps per row: rounds of 8192 addends halve the number of serial rounds of the longest row
-          k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 32, true, EPI><<<M.n_long, 32 * 32, 0, st>>>(
-              pb, M, 0, M.n_long, hot, x, xbits, (float*)y, ybits, staged, ep);
+          auto kt = k_heavy_fadd32_tma<P, T, V, IDENT, EPI>;
+          constexpr int ring_bytes = 2 * GM_TMA_ROUND * 4;
+          static bool attr = false;
+          if (!attr) {
+            GM_CUDA_OK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+            attr = true;
+          }
+          kt<<<M.n_long, GM_TMA_W * 32, ring_bytes, st>>>(pb, M, 0, M.n_long, (const float*)staged, (float*)y, ybits, ep);
           if (sc) sc->launches += 2;
           coop_begin = M.n_long;
         }
@@ -1364,14 +1543,22 @@ struct engine {
       if (n_coop > coop_begin) {
         const int cap = gm_sm_count() * 64;
         int blocks = n_coop - coop_begin < cap ? n_coop - coop_begin : cap;
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16, false, EPI><<<blocks, 16 * 32, 0, st>>>(
-            pb, M, coop_begin, n_coop, hot, x, xbits, (float*)y, ybits, nullptr, ep);
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 16, EPI><<<blocks, 16 * 32, 0, st>>>(
+            pb, M, coop_begin, n_coop, hot, x, xbits, (float*)y, ybits, ep);
         if (sc) sc->launches++;
       }
       if (M.n_heavy > n_coop) {
         int rows = M.n_heavy - n_coop;
-        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1, false, EPI><<<(rows + 3) / 4, 128, 0, st>>>(
-            pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits, nullptr, ep);
+#ifdef GM_EXPERIMENTS
+        if (getenv("GM_DBG_SERIALIZE_H1") && hs[1] != hs[0]) {  // heavy1 on its own stream but after the block-per-row kernel
+          static cudaEvent_t dbg_ev = nullptr;
+          if (!dbg_ev) cudaEventCreateWithFlags(&dbg_ev, cudaEventDisableTiming);
+          cudaEventRecord(dbg_ev, hs[0]);
+          cudaStreamWaitEvent(hs[1], dbg_ev, 0);
+        }
+#endif
+        k_heavy_fadd32<P, T, V, E, ALLACT, IDENT, 1, EPI><<<(rows + 3) / 4, 128, 0, hs[1]>>>(
+            pb, M, n_coop, M.n_heavy, hot, x, xbits, (float*)y, ybits, ep);
         if (sc) sc->launches++;
       }
     } else if constexpr (REORDER) {
@@ -1501,16 +1688,27 @@ struct engine {
         }
       }
     }
-    // heavy rows and sliced-ELL rows are disjoint: run them concurrently on two streams
-    cudaStream_t sh = gv.aux_stream ? (cudaStream_t)gv.aux_stream : st;
-    const bool fork = M.n_heavy > 0 && M.n_slices > 0 && sh != st;
-    if (fork) {
-      GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_fork, st));
-      GM_CUDA_OK(cudaStreamWaitEvent(sh, (cudaEvent_t)gv.ev_fork, 0));
-    }
+    // heavy rows and sliced-ELL rows are disjoint (rows and y words): their kernels run concurrently, on up to four
+    // streams -- every one of them alone leaves the L1->L2 request port of the SMs partly idle (latency-bound tails)
+    cudaStream_t aux[3] = {(cudaStream_t)gv.aux_stream, (cudaStream_t)gv.aux_stream2, (cudaStream_t)gv.aux_stream3};
+    cudaEvent_t joins[3] = {(cudaEvent_t)gv.ev_join, (cudaEvent_t)gv.ev_join2, (cudaEvent_t)gv.ev_join3};
+    bool used[3] = {false, false, false};
+    auto on_aux = [&](int k) -> cudaStream_t {  // stream k if the graph has it, else the nearest lower one
+      for (int j = k; j >= 0; j--)
+        if (aux[j]) { used[j] = true; return aux[j]; }
+      return st;
+    };
+    const bool fork = aux[0] != nullptr && (M.n_heavy > 0) + (M.n_slices > 0) >= 1;
+    if (fork) GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_fork, st));
+    auto enter = [&](cudaStream_t s2) -> int {
+      if (s2 != st) GM_CUDA_OK(cudaStreamWaitEvent(s2, (cudaEvent_t)gv.ev_fork, 0));
+      return 0;
+    };
     if (M.n_heavy > 0) {
-      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM, EPI>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, fork ? sh : st, sc, vecs, ep))
-        return 1;
+      const bool both = M.n_slices > 0;
+      cudaStream_t hs[2] = {both ? on_aux(0) : st, both ? on_aux(1) : (aux[0] ? on_aux(0) : st)};
+      if (enter(hs[0]) || (hs[1] != hs[0] && enter(hs[1]))) return 1;
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM, EPI>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, hs, sc, vecs, ep)) return 1;
     }
     if (M.n_slices > 0) {
       // wide slices: one per warp, deep unroll (a lane's chain waits for loads once per UNROLL
@@ -1531,19 +1729,22 @@ struct engine {
       }
       if (M.n_slices > nw) {
         const int warps = (M.n_slices - nw + spw_tail - 1) / spw_tail;
+        cudaStream_t ts = (nw > 0 && aux[2]) ? on_aux(2) : st;  // the narrow tail beside the wide slices
+        if (enter(ts)) return 1;
         if constexpr (LASTW)
-          k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(warps + 7) / 8, 256, 0, st>>>(
+          k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(warps + 7) / 8, 256, 0, ts>>>(
               pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits);
         else
-          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN, EPI><<<(warps + 7) / 8, 256, 0, st>>>(
+          k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN, EPI><<<(warps + 7) / 8, 256, 0, ts>>>(
               pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits, ep);
         if (sc) sc->launches++;
       }
     }
-    if (fork) {
-      GM_CUDA_OK(cudaEventRecord((cudaEvent_t)gv.ev_join, sh));
-      GM_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)gv.ev_join, 0));
-    }
+    for (int k = 0; k < 3; k++)
+      if (used[k]) {
+        GM_CUDA_OK(cudaEventRecord(joins[k], aux[k]));
+        GM_CUDA_OK(cudaStreamWaitEvent(st, joins[k], 0));
+      }
     if (sc) sc->edges += M.nnz;
     GM_CUDA_OK(cudaGetLastError());
     return 0;

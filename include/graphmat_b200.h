@@ -92,6 +92,8 @@ typedef struct gm_graph_view {
   void* stream;                 /* cudaStream_t all work is ordered on */
   void* aux_stream;             /* second stream: heavy rows run beside the sliced-ELL rows */
   void* ev_fork; void* ev_join; /* cudaEvent_t pair ordering the two streams */
+  void* aux_stream2; void* aux_stream3; /* more of the same: warp-per-row heavy rows, narrow sliced-ELL tail */
+  void* ev_join2; void* ev_join3;
   int hot_limit;                /* x indices below this are gathered with an L1-resident hint */
   gm_graph* owner;              /* the handle this view was taken from */
   int push_divisor;             /* sparse-frontier path when frontier entries * divisor <= nnz; 0 = never */

@@ -50,7 +50,7 @@ def test_host_fold_is_bit_exact():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("warps", [1, 16])
+@pytest.mark.parametrize("warps", [1, 16, 32])  # 32: the TMA-streamed kernel of the staged longest rows
 def test_device_fold_is_bit_exact(warps):
     for i, a in enumerate(cases(2, 70, 20000)):
         r = capi.fold_f32_device(a, warps=warps, offset=i % 9)
