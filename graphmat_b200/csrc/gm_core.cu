@@ -591,7 +591,13 @@ static int graph_common_alloc(gm_graph* g) {
   CK(cudaMemsetAsync(g->active, 0, (size_t)(g->n_pad >> 5) * 4, st));  // active->setAll(false), Graph.h:236-237
   if (dalloc(&g->d_flags, 16)) return 1;
   CK(cudaMemsetAsync(g->d_flags, 0, 64, st));
-  CK(cudaStreamCreateWithFlags(&g->aux_stream, cudaStreamNonBlocking));
+  {
+    // the auxiliary stream carries the latency-bound kernels of a pass (long rows): highest priority, so that their
+    // few large blocks are placed before the thousands of sliced-ELL blocks that would otherwise fill every SM
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&g->aux_stream, cudaStreamNonBlocking, getenv("GM_NO_PRIORITY") ? lo : hi));
+  }
   CK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   if (const char* e = getenv("GM_HOT_LIMIT")) g->hot_limit = atoi(e);

@@ -1512,7 +1512,7 @@ struct engine {
   template <bool ALLACT, bool NEEDVP, bool IDENT, bool ACCUM, bool EPI>
   static int heavy_rows(const prog_bytes<P>& pb, const gm_matrix_view& M, int hot, const T* x, const unsigned* xbits,
                         const V* vp, U* y, unsigned* ybits, cudaStream_t const (&hs)[2], step_counters* sc, gm_vectors* vecs,
-                        const EP& ep) {
+                        const EP& ep, cudaEvent_t staged_ev = nullptr, bool* staged_recorded = nullptr) {
     constexpr bool FADD = is_fadd32<P>::value && std::is_same<U, float>::value && !NEEDVP && !ACCUM;
     cudaStream_t st = hs[0];
     if constexpr (FADD) {
@@ -1528,6 +1528,10 @@ struct engine {
           T* staged = (T*)scratch;
           const long long groups = (M.long_entries + 7) / 8;
           k_stage_rows<T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(M.h_col, M.long_entries, x, hot, staged);
+          if (staged_ev) {  // the caller holds the sliced-ELL kernels back until here: see mult_t
+            GM_CUDA_OK(cudaEventRecord(staged_ev, st));
+            *staged_recorded = true;
+          }
           auto kt = k_heavy_fadd32_tma<P, T, V, IDENT, EPI>;
           constexpr int ring_bytes = 2 * GM_TMA_ROUND * 4;
           static bool attr = false;
@@ -1708,7 +1712,16 @@ struct engine {
       const bool both = M.n_slices > 0;
       cudaStream_t hs[2] = {both ? on_aux(0) : st, both ? on_aux(1) : (aux[0] ? on_aux(0) : st)};
       if (enter(hs[0]) || (hs[1] != hs[0] && enter(hs[1]))) return 1;
-      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM, EPI>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, hs, sc, vecs, ep)) return 1;
+      // The 1024-thread blocks of the staged long-row fold each need a whole SM.  Enqueued behind thousands of
+      // sliced-ELL blocks they would only start when those drain (measured: the pass of rank 0 of 8 then lasts
+      // the SUM of the two chains).  So the sliced-ELL kernels wait for the staging gather (which fills the GPU by
+      // itself) and the high-priority long-row blocks are placed first, on empty SMs.
+      bool staged_recorded = false;
+      cudaEvent_t mid = (hs[0] != st && !getenv("GM_NO_HOLD")) ? (cudaEvent_t)gv.ev_join2 : nullptr;
+      if (heavy_rows<ALLACT, NEEDVP, IDENT, ACCUM, EPI>(pb, M, hot, x, vv.x_bits, vp, y, vv.y_bits, hs, sc, vecs, ep, mid,
+                                                         &staged_recorded))
+        return 1;
+      if (staged_recorded) GM_CUDA_OK(cudaStreamWaitEvent(st, mid, 0));
     }
     if (M.n_slices > 0) {
       // wide slices: one per warp, deep unroll (a lane's chain waits for loads once per UNROLL
