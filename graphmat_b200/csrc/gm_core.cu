@@ -1160,6 +1160,18 @@ static int build_push(gm_graph* g, gm_matrix& M) {
 
 static gm_matrix* which_matrix(gm_graph* g, int which) { return which == 0 ? &g->A : &g->AT; }
 
+static void push_free(gm_matrix& M) {
+  cudaFree(M.c_ptr); cudaFree(M.c_row); cudaFree(M.c_rank); cudaFree(M.c_val); cudaFree(M.big_cols);
+  M.c_ptr = nullptr; M.c_row = nullptr; M.c_rank = nullptr; M.c_val = nullptr; M.big_cols = nullptr;
+  M.n_big_cols = 0;
+  M.push_built = false;
+}
+extern "C" int gm_graph_edges_changed(gm_graph* g) {
+  CK(cudaStreamSynchronize(g->stream));
+  push_free(g->A);
+  push_free(g->AT);
+  return 0;
+}
 extern "C" int gm_graph_set_push_policy(gm_graph* g, int divisor, long long min_nnz) {
   g->push_divisor = divisor < 0 ? 0 : divisor;
   g->push_min_nnz = min_nnz < 0 ? 0 : min_nnz;

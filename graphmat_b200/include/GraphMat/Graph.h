@@ -14,12 +14,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "edgelist.h"
 #include "graphmat_b200.h"
+#ifdef __CUDACC__
+#include <type_traits>
+
+#include "gm_vertex_ops.cuh"
+#endif
 
 namespace GraphMat {
 
@@ -59,6 +65,7 @@ class Graph {
   std::shared_ptr<detail::vp_mirror<V> > mirror;
   std::vector<int> e_src, e_dst;  // kept so that shareVertexProperty can rebuild in the owner's placement
   std::vector<E> e_val;
+  bool edges_on_host_stale = false;
 
   static int ref_threads() {
     const char* e = getenv("GM_REF_THREADS");
@@ -126,6 +133,7 @@ class Graph {
   void ReadGraphMatBin(const char*) { unsupported("ReadGraphMatBin"); }
   void WriteGraphMatBin(const char*) { unsupported("WriteGraphMatBin"); }
   void getEdgelist(GraphMat::edgelist_t<E>& out) {
+    if (edges_on_host_stale) unsupported("getEdgelist after a device-side applyToAllEdges");
     out = GraphMat::edgelist_t<E>(nvertices, nvertices, (int)nnz);
     for (long long i = 0; i < nnz; i++) out.edges[i] = GraphMat::edge_t<E>(e_src[i], e_dst[i], e_val[i]);
   }
@@ -152,16 +160,11 @@ class Graph {
   bool vertexNodeOwner(const int v) const { return gm_graph_vertex_owner(handle, v) == 0; }
   void saveVertexproperty(std::string fname, bool includeHeader = true) const {
     const_cast<Graph*>(this)->pull();
-    FILE* f = fopen((fname + "0").c_str(), "w");
-    if (!f) return;
-    if (includeHeader) fprintf(f, "%d %d\n", nvertices, nvertices);
-    for (int i = 0; i < nvertices; i++) {
-      fprintf(f, "%d ", i + 1);
-      const unsigned char* b = reinterpret_cast<const unsigned char*>(&mirror->host[i]);
-      for (size_t k = 0; k < sizeof(V); k++) fprintf(f, "%02x", b[k]);
-      fprintf(f, "\n");
-    }
-    fclose(f);
+    // the reference's text format (DenseSegment::save, include/GMDP/vectors/DenseSegment.h): "<id> <value>" lines
+    // through V's operator<<, behind an "<n> <count>" header; one file per rank, this build is rank 0
+    std::ofstream out((fname + "0").c_str());
+    if (includeHeader) out << nvertices << " " << nvertices << "\n";
+    for (int i = 0; i < nvertices; i++) out << (i + 1) << " " << mirror->host[i] << "\n";
   }
   void reset() {
     setAllInactive();
@@ -212,6 +215,29 @@ class Graph {
     detail::check(gm_graph_set_edge_values(handle, nnz, e_src.data(), e_dst.data(), e_val.data()),
                   "gm_graph_set_edge_values");
   }
+
+#ifdef __CUDACC__
+  // ---- the same three, on the DEVICE, for GM_HD functors (gm_vertex_ops.cuh): no pull of the vertex array, the
+  //      functor's state replaces `param`.  Function pointers keep resolving to the host overloads above. ----
+  template <class F, class = typename std::enable_if<!std::is_pointer<F>::value && !std::is_function<F>::value>::type>
+  void applyToAllVertices(F f) {
+    push();
+    detail::check(gm::map_vertices<V, F>(handle, f), "applyToAllVertices (device)");
+    invalidate();
+  }
+  template <class T, class M, class R,
+            class = typename std::enable_if<!std::is_pointer<M>::value && !std::is_function<M>::value>::type>
+  void applyReduceAllVertices(T* val, M map, R reduce) {
+    push();
+    detail::check(gm::map_reduce_vertices<V, T, M, R>(handle, val, map, reduce), "applyReduceAllVertices (device)");
+  }
+  template <class F, class = typename std::enable_if<!std::is_pointer<F>::value && !std::is_function<F>::value>::type>
+  void applyToAllEdges(F f) {
+    push();
+    detail::check(gm::apply_edges<V, E, F>(handle, f), "applyToAllEdges (device)");
+    edges_on_host_stale = true;  // e_val no longer mirrors the device matrices (getEdgelist refuses)
+  }
+#endif
 
   // ---- used by run_graph_program ----
   void push() {  // host writes -> device

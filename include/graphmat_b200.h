@@ -148,6 +148,8 @@ int gm_graph_destroy(gm_graph* g);
  * in the order and with the (src, dst) the graph was created from (host arrays).  Both operand matrices are
  * refilled in place; vertex properties, the active set and the vertex placement are kept. */
 int gm_graph_set_edge_values(gm_graph* g, long long nnz, const int* src, const int* dst, const void* val);
+int gm_graph_edges_changed(gm_graph* g);  /* edge values were rewritten in place on the device (device-side
+                                             applyToAllEdges): drop the column-major companion, it is rebuilt on demand */
 int gm_graph_view_get(const gm_graph* g, gm_graph_view* out);
 int gm_graph_synchronize(const gm_graph* g);
 

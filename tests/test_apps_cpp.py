@@ -99,7 +99,8 @@ def test_sgd_app_on_ratings7(tmp_path):
 def test_apply_edges_cpp(n):
     """test/test_apply_edges.cpp of the reference (applyToAllEdges + getEdgelist) on the C++ mirror, and SSSP over
     the rewritten weights (the device matrices carry them)"""
-    assert "apply_edges ok" in run("ApplyEdgesCheck", n)
+    out = run("ApplyEdgesCheck", n)
+    assert "apply_edges ok" in out and "device functors ok" in out
 
 
 @pytest.mark.parametrize("policy", ["default", "always_push", "never_push"])
