@@ -32,6 +32,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "--workload" in sys.argv and "deltastepping" in sys.argv and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # torchrun pins OMP_NUM_THREADS=1; the host-side RMAT generator + light/heavy split of this workload is OpenMP code
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
 
 import numpy as np  # noqa: E402
 

@@ -340,7 +340,7 @@ def run(c, args, B):
             G.set_all_active()
             return G.run(p_sgd, state, args.iters, tmp)
 
-        dev_ms, spmv_ms, wall_ms, launches, _ = B.timed_steps(c, args, step)
+        dev_ms, spmv_ms, wall_ms, launches, sgd_clocks = B.timed_steps(c, args, step)
         B.barrier(c)
         t0 = time.perf_counter()
         esteps = max(1, min(args.steps, 2))
@@ -370,6 +370,7 @@ def run(c, args, B):
         roof["frac_gather_inclusive"] = roof["achieved_gather_inclusive"] / peak
         extra = {"ratings": nr, "K": K, "iterations_per_step": args.iters}
         sampler.stop_flag = True
+        sampler.summary = lambda: sgd_clocks
         tmp.close(); G.close()
         dtype = "f64"
 
