@@ -2,7 +2,10 @@
 // getEdgelist) on the device engine, plus a check that the DEVICE matrices carry the new values:
 // SSSP over the rewritten weights must equal a host Bellman-Ford over the same weights.
 // usage: ApplyEdgesCheck <N>      prints "apply_edges ok" on success
+#include <unistd.h>
+
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "GraphMatRuntime.h"
@@ -146,6 +149,31 @@ int main(int argc, char* argv[]) {
   rc = check_device(R);
   if (rc) { printf("apply_edges device functors FAILED (%d)\n", rc); return 1; }
   printf("device functors ok\n");
+  {  // snapshot round trip (Graph.h:152-208 re-specified): same graph back, SSSP distances equal
+    GraphMat::edgelist_t<int> R2(N, N, nnz);
+    for (int i = 0; i < nnz; i++) R2.edges[i] = R.edges[i];
+    GraphMat::Graph<SSSP_vertex_type, int> G1, G2;
+    G1.ReadEdgelist(R2);
+    char path[256];
+    snprintf(path, sizeof path, "/tmp/gm_snapshot_%d_", (int)getpid());
+    G1.WriteGraphMatBin(path);
+    G2.ReadGraphMatBin(path);
+    remove((std::string(path) + "0").c_str());
+    if (G2.getNumberOfVertices() != N || G2.nnz != nnz) { printf("snapshot FAILED (shape)\n"); return 1; }
+    SSSP_vertex_type zero;
+    zero.distance = 0;
+    GraphMat::Graph<SSSP_vertex_type, int>* gs[2] = {&G1, &G2};
+    for (auto* g : gs) {
+      g->setAllInactive();
+      g->setVertexproperty(1, zero);
+      g->setActive(1);
+      SSSP<int> prog;
+      GraphMat::run_graph_program(&prog, *g, GraphMat::UNTIL_CONVERGENCE);
+    }
+    for (int i = 1; i <= N; i++)
+      if (G1.getVertexproperty(i).distance != G2.getVertexproperty(i).distance) { printf("snapshot FAILED (%d)\n", i); return 1; }
+    printf("snapshot ok\n");
+  }
   R.clear();
   printf("apply_edges ok\n");
   return 0;

@@ -15,6 +15,16 @@ void CheckBucketNotEmpty(DeltaSteppingDS* v, int* result, void* param) {
 }
 template <typename T>
 void Add(const T& a, const T& b, T* c, void* param) { *c = a + b; }
+// The same map / reduce as GM_HD functors (`param` becomes a member): applyReduceAllVertices then runs on the
+// device, one kernel and four bytes back per bucket instead of a pull of the whole vertex array (GM_HOST_REDUCE=1
+// keeps the reference's function-pointer call, for comparison).
+struct CheckBucketNotEmptyFn {
+  int bid;
+  GM_HD void operator()(DeltaSteppingDS* v, int* result) const { *result = (v->bucket >= bid && v->bucket < 0x7fffffff) ? 1 : 0; }
+};
+struct AddIntFn {
+  GM_HD void operator()(const int& a, const int& b, int* c) const { *c = a + b; }
+};
 bool less_than_delta(GraphMat::edge_t<int> e, void* param) { return e.val <= *(int*)param; }
 bool greater_than_delta(GraphMat::edge_t<int> e, void* param) { return e.val > *(int*)param; }
 
@@ -52,7 +62,13 @@ void run_deltastepping(const char* filename, int delta, int v, const char* dump)
     GraphMat::run_graph_program(&deltastep, G2, 1, &ds_ts);
     deltastep.bid++;
     bucket_not_empty = 0;
-    G.applyReduceAllVertices(&bucket_not_empty, CheckBucketNotEmpty, Add<int>, (void*)&deltastep.bid);
+    if (getenv("GM_HOST_REDUCE")) {
+      G.applyReduceAllVertices(&bucket_not_empty, CheckBucketNotEmpty, Add<int>, (void*)&deltastep.bid);
+    } else {
+      CheckBucketNotEmptyFn map;
+      map.bid = deltastep.bid;
+      G.applyReduceAllVertices(&bucket_not_empty, map, AddIntFn());
+    }
   } while (bucket_not_empty != 0);
   printf("Time = %.3f ms \n", now_ms() - t0);
   GraphMat::graph_program_clear(ds_ts);

@@ -265,9 +265,9 @@ extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, 
   long long* dptr = nullptr;
   unsigned* dbits = nullptr;
   long long tot = n + offset;
-  cudaMalloc(&dx, (tot + 2 * gm::GM_TMA_ROUND) * 4); cudaMalloc(&dcol, (tot + 16) * 4); cudaMalloc(&dval, (tot + 16) * 4);
+  cudaMalloc(&dx, (tot + (gm::GM_TMA_BUFS + 1) * gm::GM_TMA_ROUND) * 4); cudaMalloc(&dcol, (tot + 16) * 4); cudaMalloc(&dval, (tot + 16) * 4);
   cudaMalloc(&dptr, 16); cudaMalloc(&dy, 4 * 32); cudaMalloc(&dbits, 4);
-  cudaMemset(dx, 0, (tot + 2 * gm::GM_TMA_ROUND) * 4);
+  cudaMemset(dx, 0, (tot + (gm::GM_TMA_BUFS + 1) * gm::GM_TMA_ROUND) * 4);
   cudaMemcpy(dx + offset, a, n * 4, cudaMemcpyHostToDevice);
   cudaMemset(dval, 0, (tot + 16) * 4);
   k_iota<<<(unsigned)((tot + 16 + 255) / 256), 256>>>(dcol, tot + 16);
@@ -282,8 +282,8 @@ extern "C" int gm_debug_fold_f32_device(const float* a, long long n, int warps, 
   gm::prog_bytes<P> pb = gm::pack(prog);
   if (warps == 32) {  // the TMA-streamed fold of the staged longest rows: dx is its own staging array
     auto kt = gm::k_heavy_fadd32_tma<P, float, PR, true, false>;
-    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * gm::GM_TMA_ROUND * 4);
-    kt<<<1, gm::GM_TMA_W * 32, 2 * gm::GM_TMA_ROUND * 4>>>(pb, M, 0, 1, dx, dy, dbits, gm::epilogue<float, PR>());
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, gm::GM_TMA_BUFS * gm::GM_TMA_ROUND * 4);
+    kt<<<1, gm::GM_TMA_W * 32, gm::GM_TMA_BUFS * gm::GM_TMA_ROUND * 4>>>(pb, M, 0, 1, dx, dy, dbits, gm::epilogue<float, PR>());
   } else if (warps == 1) gm::k_heavy_fadd32<P, float, PR, int, true, true, 1><<<1, 128>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
   else gm::k_heavy_fadd32<P, float, PR, int, true, true, 16><<<1, 512>>>(pb, M, 0, 1, 1 << 15, dx, nullptr, dy, dbits);
   cudaError_t e = cudaDeviceSynchronize();

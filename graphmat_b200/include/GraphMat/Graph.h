@@ -6,15 +6,15 @@
 // so they cost O(1) each instead of one PCIe round trip each.
 //
 // Differences a maintainer should know: E must be a 4-byte type; the
-// GraphMat-binary snapshot format (ReadGraphMatBin / WriteGraphMatBin, Boost archives) is
-// outside this hot-path build and prints-and-exits like the reference's error convention;
-// applyToAllEdges evaluates its (host) function on the host and refills the device matrices.
+// GraphMat-binary snapshot (ReadGraphMatBin / WriteGraphMatBin) is re-specified without Boost;
+// applyToAllEdges & co. evaluate host function pointers on the host and GM_HD functors on the device.
 #ifndef GRAPHMAT_B200_GRAPH_H
 #define GRAPHMAT_B200_GRAPH_H
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -130,8 +130,61 @@ class Graph {
     ReadEdgelist(A_edges);
     A_edges.clear();
   }
-  void ReadGraphMatBin(const char*) { unsupported("ReadGraphMatBin"); }
-  void WriteGraphMatBin(const char*) { unsupported("WriteGraphMatBin"); }
+  // Graph.h:152-208.  The reference's snapshot is a Boost binary archive of its DCSC tiles (A, AT) and the OpenMP
+  // thread count; Boost is not part of this build and the tiles are not this engine's layout, so the snapshot is
+  // re-specified: little-endian  "GMB200\0\1" | int nvertices | int num_threads | int sizeof(E) |
+  // long long nnz | nnz x (int src, int dst, E val), public ids.  Same contract as the reference: one file per rank
+  // (<filename>0), vertex properties and the active set are NOT part of it (a loaded graph starts from V() /
+  // inactive), and loading under a different thread count is refused because it would change the fold order.
+  void WriteGraphMatBin(const char* filename) {
+    const std::string fn = std::string(filename) + "0";
+    std::cout << "Writing file " << fn << std::endl;
+    std::ofstream out(fn.c_str(), std::ios::out | std::ios::binary);
+    if (!out) { printf("graphmat_b200: cannot write %s\n", fn.c_str()); exit(1); }
+    if (edges_on_host_stale) unsupported("WriteGraphMatBin after a device-side applyToAllEdges");
+    const char magic[8] = {'G', 'M', 'B', '2', '0', '0', 0, 1};
+    const int se = (int)sizeof(E);
+    out.write(magic, 8);
+    out.write((const char*)&nvertices, 4);
+    out.write((const char*)&num_threads, 4);
+    out.write((const char*)&se, 4);
+    out.write((const char*)&nnz, 8);
+    for (long long i = 0; i < nnz; i++) {
+      out.write((const char*)&e_src[i], 4);
+      out.write((const char*)&e_dst[i], 4);
+      out.write((const char*)&e_val[i], sizeof(E));
+    }
+  }
+  void ReadGraphMatBin(const char* filename) {
+    const std::string fn = std::string(filename) + "0";
+    std::cout << "Reading file " << fn << std::endl;
+    std::ifstream in(fn.c_str(), std::ios::in | std::ios::binary);
+    char magic[8] = {0};
+    int nv = 0, nt = 0, se = 0;
+    long long nz = 0;
+    in.read(magic, 8);
+    in.read((char*)&nv, 4);
+    in.read((char*)&nt, 4);
+    in.read((char*)&se, 4);
+    in.read((char*)&nz, 8);
+    if (!in || memcmp(magic, "GMB200", 6) != 0 || se != (int)sizeof(E) || nv <= 0 || nz < 0) {
+      std::cout << "Error reading file - not a graphmat_b200 snapshot of this edge type" << std::endl;
+      exit(1);
+    }
+    if (nt != num_threads) {
+      std::cout << "Error reading file - mismatch in number of OpenMP threads used in load vs save graph" << std::endl;
+      exit(1);
+    }
+    GraphMat::edgelist_t<E> E_(nv, nv, (int)nz);
+    for (long long i = 0; i < nz; i++) {
+      in.read((char*)&E_.edges[i].src, 4);
+      in.read((char*)&E_.edges[i].dst, 4);
+      in.read((char*)&E_.edges[i].val, sizeof(E));
+    }
+    if (!in) { std::cout << "Error reading file - truncated snapshot" << std::endl; exit(1); }
+    ReadEdgelist(E_);
+    E_.clear();
+  }
   void getEdgelist(GraphMat::edgelist_t<E>& out) {
     if (edges_on_host_stale) unsupported("getEdgelist after a device-side applyToAllEdges");
     out = GraphMat::edgelist_t<E>(nvertices, nvertices, (int)nnz);

@@ -1003,12 +1003,16 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
 // array with BULK ASYNC COPIES (cp.async.bulk, the TMA engine) into a double-buffered shared-memory ring, one
 // mbarrier per buffer, so the copy of round r+1 runs under the fold of round r and a round costs shared-memory
 // reads instead of an L2 round trip.  A round is GM_TMA_ROUND = 32 warps x 2 chunks x 256 addends; every warp
-// scans its chunks under the binade of the block's entry value and hands ONE composed map to the block-level
-// scan, so the three block barriers of the protocol are paid once per 16 K addends (8 K before).  Same addends,
-// same order, same exactness argument as k_heavy_fadd32 (all q >= 0: the exit value decides).
+// scans its chunks under the binade of the block's entry value and publishes ONE composed map; after a single
+// block barrier EVERY warp scans the 32 published maps itself and so knows the new running value (held in
+// registers by all threads) -- a round that stays inside its binade costs one barrier (k_heavy_fadd32: three, with
+// warp 0 scanning while the others wait).  Same addends, same order, same exactness argument as k_heavy_fadd32
+// (all q >= 0: the exit value decides).
 constexpr int GM_TMA_W = 32;                                   // warps per block
 constexpr int GM_TMA_CH = 2;                                   // 256-addend chunks per warp and round
 constexpr int GM_TMA_ROUND = GM_TMA_W * 256 * GM_TMA_CH;       // addends per round (16384 -> 64 KB per buffer)
+constexpr int GM_TMA_BUFS = 3;                                 // ring depth: two rounds in flight behind the one being folded
+constexpr int GM_TMA_PARTS = 8;                                // bulk copies per round (8 KB each)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -1033,56 +1037,73 @@ __global__ void __launch_bounds__(GM_TMA_W * 32)
     k_heavy_fadd32_tma(prog_bytes<P> pb, gm_matrix_view M, int row_begin, int row_end, const float* __restrict__ staged,
                        float* __restrict__ y, unsigned* __restrict__ ybits, epilogue<T, V> ep) {
   static_assert(sizeof(T) == 4, "staged rows hold 4-byte messages");
-  constexpr int W = GM_TMA_W, CH = GM_TMA_CH;
+  constexpr int W = GM_TMA_W, CH = GM_TMA_CH, NB = GM_TMA_BUFS;
   extern __shared__ __align__(128) unsigned char tma_smem[];
-  float* ring = reinterpret_cast<float*>(tma_smem);  // 2 buffers of GM_TMA_ROUND floats
-  __shared__ __align__(8) unsigned long long bar[2];
-  __shared__ float sm_s;
-  __shared__ int sm_have, sm_fail;
-  __shared__ unsigned sm_d0[W], sm_d1[W], sm_bad[W];
+  float* ring = reinterpret_cast<float*>(tma_smem);  // NB buffers of GM_TMA_ROUND floats
+  __shared__ __align__(8) unsigned long long bar[NB];
+  // published values are double-buffered by generation: a warp may already write generation g + 1 while a slower
+  // warp still reads generation g (a writer of g + 2 has passed the barrier of g + 1, which every reader of g reaches
+  // only after its read)
+  __shared__ float sm_s[2];
+  __shared__ int sm_have[2];
+  __shared__ unsigned sm_d0[2][W], sm_d1[2][W], sm_bad[2][W];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int i = 0; i < NB; i++) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  unsigned phase[2] = {0u, 0u};
+  unsigned phases = 0u;  // bit i = the parity buffer i's mbarrier completes next
+  unsigned gen = 0;
+  // one round = GM_TMA_ROUND floats, fetched as GM_TMA_PARTS bulk copies (lanes of warp 0) on one mbarrier, so the
+  // copy engine has several requests in flight; rounds r+1 .. r+NB-1 are in flight while round r is folded
+  auto issue = [&](int b, const float* src) {
+    if (w == 0) {
+      if (lane == 0) mbar_expect_tx(&bar[b], GM_TMA_ROUND * 4);
+      __syncwarp();
+      if (lane < GM_TMA_PARTS) {
+        constexpr int part = GM_TMA_ROUND / GM_TMA_PARTS;
+        tma_load_1d(ring + (size_t)b * GM_TMA_ROUND + lane * part, src + lane * part, part * 4, &bar[b]);
+      }
+    }
+  };
   for (int slot = row_begin + blockIdx.x; slot < row_end; slot += gridDim.x) {
     const long long beg = __ldg(M.h_ptr + slot), end = __ldg(M.h_ptr + slot + 1);
     const int vtx = IDENT ? slot : __ldg(M.slot_vertex + slot);
-    if (threadIdx.x == 0) { sm_s = 0.f; sm_have = 0; }
+    // the running value of the fold, held by EVERY thread (block-uniform): the fast path never goes through memory
+    float s = 0.f;
+    bool have = false;
     const long long k_first = beg & ~7ll;  // 32-byte aligned start: the staging array is 256-byte aligned
     const long long n_rounds = (end - k_first + GM_TMA_ROUND - 1) / GM_TMA_ROUND;
-    // everybody is done reading the ring (previous row) before the async proxy overwrites it
-    __syncthreads();
-    if (threadIdx.x == 0 && n_rounds > 0) {
-      mbar_expect_tx(&bar[0], GM_TMA_ROUND * 4);
-      tma_load_1d(ring, staged + k_first, GM_TMA_ROUND * 4, &bar[0]);
-    }
+    __syncthreads();  // everybody is done reading the ring (previous row) before the async proxy overwrites it
+    for (int q = 0; q < NB - 1 && q < n_rounds; q++) issue(q, staged + k_first + (long long)q * GM_TMA_ROUND);
+    int cur = 0;
     for (long long r = 0; r < n_rounds; r++) {
-      const int cur = (int)(r & 1);
       const long long k0 = k_first + r * GM_TMA_ROUND;
-      if (threadIdx.x == 0 && r + 1 < n_rounds) {  // buffer cur^1 was released by the barrier that ended round r-1
-        mbar_expect_tx(&bar[cur ^ 1], GM_TMA_ROUND * 4);
-        tma_load_1d(ring + (cur ^ 1) * GM_TMA_ROUND, staged + k0 + GM_TMA_ROUND, GM_TMA_ROUND * 4, &bar[cur ^ 1]);
-      }
-      mbar_wait(&bar[cur], phase[cur]);
-      phase[cur] ^= 1u;
-      const float* buf = ring + cur * GM_TMA_ROUND;
+      // the buffer of round r + NB - 1 is the one round r - 1 used, and every path of a round ends with a block barrier
+      // behind its last read
+      if (r + NB - 1 < n_rounds) issue((cur + NB - 1) % NB, staged + k0 + (long long)(NB - 1) * GM_TMA_ROUND);
+      mbar_wait(&bar[cur], (phases >> cur) & 1u);
+      phases ^= 1u << cur;
+      const float* buf = ring + (size_t)cur * GM_TMA_ROUND;
+      cur = (cur + 1) % NB;
       // chunk c of warp w: addends [k0 + (w*CH + c)*256 + lane*8, +8)
       auto load = [&](int c, float (&v)[8], unsigned& vmask) {
         const int off = (w * CH + c) * 256 + lane * 8;
         const float4 a = *reinterpret_cast<const float4*>(buf + off);
-        const float4 b = *reinterpret_cast<const float4*>(buf + off + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        vmask = 0;
+        const float4 b4 = *reinterpret_cast<const float4*>(buf + off + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
         const long long i0 = k0 + off;
+        if (i0 >= beg && i0 + 8 <= end) {
+          vmask = 0xffu;
+        } else {
+          vmask = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if (i0 + j >= beg && i0 + j < end) vmask |= 1u << j;
-          else v[j] = 0.f;  // outside the row: +0, the identity of the fold
+          for (int j = 0; j < 8; j++) {
+            if (i0 + j >= beg && i0 + j < end) vmask |= 1u << j;
+            else v[j] = 0.f;  // outside the row: +0, the identity of the fold
+          }
         }
       };
       const long long span = end - k0;
@@ -1090,12 +1111,11 @@ __global__ void __launch_bounds__(GM_TMA_W * 32)
       if (nw > W) nw = W;
       int first = 0;  // warps [first, nw) are still to be applied
       while (first < nw) {
-        const float s = sm_s;
-        const bool have = sm_have != 0;
         fx::binade b;
         const bool hot = have && fx::binade_of(s, b);  // block-uniform
+        const unsigned g = gen & 1u;
         if (!hot) {
-          // no usable accumulator yet: warp `first` folds its chunks alone (exact for any input)
+          // no usable accumulator yet: warp `first` folds its chunks alone (exact for any input) and publishes
           if (w == first) {
             float sq = s;
             bool hq = have;
@@ -1105,10 +1125,13 @@ __global__ void __launch_bounds__(GM_TMA_W * 32)
               load(c, v, vmask);
               fx::warp_fold(v, vmask, sq, hq, lane);
             }
-            if (lane == 0) { sm_s = sq; sm_have = hq ? 1 : 0; }
+            if (lane == 0) { sm_s[g] = sq; sm_have[g] = hq ? 1 : 0; }
           }
-          first++;
           __syncthreads();
+          s = sm_s[g];
+          have = sm_have[g] != 0;
+          gen++;
+          first++;
           continue;
         }
         if (w >= first && w < nw) {
@@ -1119,41 +1142,51 @@ __global__ void __launch_bounds__(GM_TMA_W * 32)
             float v[8];
             unsigned vmask;
             load(c, v, vmask);
-            fx::qmap mine = fx::identity();
+            // fast path (no addend of the chunk is a tie): the chunk is the translation by the sum of its q0,
+            // one integer add per addend and one warp reduction -- only the warp TOTAL is needed here
+            bool tie = false;
+            unsigned sum = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
-            const fx::qmap incl = fx::warp_scan(mine, lane);
+            for (int j = 0; j < 8; j++) sum += fx::quantize_q0(v[j], b, bad, tie);  // < 2^26 per lane
             fx::qmap tot;
-            tot.d0 = __shfl_sync(0xffffffffu, incl.d0, 31);
-            tot.d1 = __shfl_sync(0xffffffffu, incl.d1, 31);
+            if (!__any_sync(0xffffffffu, tie)) {
+              const unsigned total = __reduce_add_sync(0xffffffffu, sum);  // 32 lanes x < 2^26: no overflow
+              tot.d0 = tot.d1 = total > fx::kSat ? fx::kSat : total;
+            } else {
+              fx::qmap mine = fx::identity();
+#pragma unroll
+              for (int j = 0; j < 8; j++) mine = fx::compose(mine, fx::quantize(v[j], b, bad));
+              const fx::qmap incl = fx::warp_scan(mine, lane);
+              tot.d0 = __shfl_sync(0xffffffffu, incl.d0, 31);
+              tot.d1 = __shfl_sync(0xffffffffu, incl.d1, 31);
+            }
             wt = fx::compose(wt, tot);
           }
           const unsigned anybad = __ballot_sync(0xffffffffu, bad);
-          if (lane == 31) { sm_d0[w] = wt.d0; sm_d1[w] = wt.d1; sm_bad[w] = anybad; }
+          if (lane == 31) { sm_d0[g][w] = wt.d0; sm_d1[g][w] = wt.d1; sm_bad[g][w] = anybad; }
         }
-        __syncthreads();
-        if (w == 0) {
-          fx::qmap t = fx::identity();
-          bool bd = false;
-          if (lane >= first && lane < nw) { t.d0 = sm_d0[lane]; t.d1 = sm_d1[lane]; bd = sm_bad[lane] != 0; }
-          t = fx::warp_scan(t, lane);
-          const unsigned m_after = fx::apply(t, b.m);
-          const bool over = (lane >= first && lane < nw) && (bd || m_after >= (1u << 24));
-          const unsigned fail = __ballot_sync(0xffffffffu, over);
-          unsigned m_prev = __shfl_up_sync(0xffffffffu, m_after, 1);
-          if (lane == 0) m_prev = b.m;
-          if (fail == 0) {
-            if (lane == nw - 1) { sm_s = __fmul_rn(__uint2float_rn(m_after), b.u); sm_fail = -1; }
-          } else {
-            const int f = __ffs(fail) - 1;
-            if (lane == f) { sm_s = __fmul_rn(__uint2float_rn(m_prev), b.u); sm_fail = f; }
-          }
+        __syncthreads();  // the ONLY block barrier of a round that stays inside its binade
+        // every warp scans the W totals itself (same inputs, same result): no second barrier, no broadcast
+        fx::qmap t = fx::identity();
+        bool bd = false;
+        if (lane >= first && lane < nw) { t.d0 = sm_d0[g][lane]; t.d1 = sm_d1[g][lane]; bd = sm_bad[g][lane] != 0; }
+        t = fx::warp_scan(t, lane);
+        const unsigned m_after = fx::apply(t, b.m);
+        const bool over = (lane >= first && lane < nw) && (bd || m_after >= (1u << 24));
+        const unsigned fail = __ballot_sync(0xffffffffu, over);
+        gen++;
+        if (fail == 0) {
+          const unsigned m_end = __shfl_sync(0xffffffffu, m_after, nw - 1);
+          s = __fmul_rn(__uint2float_rn(m_end), b.u);
+          break;
         }
-        __syncthreads();
-        const int f = sm_fail;
-        if (f < 0) break;
+        const int f = __ffs(fail) - 1;
+        unsigned m_prev = __shfl_up_sync(0xffffffffu, m_after, 1);
+        if (lane == 0) m_prev = b.m;
+        m_prev = __shfl_sync(0xffffffffu, m_prev, f);
+        const unsigned g2 = gen & 1u;
         if (w == f) {  // the warp whose exit would leave the binade: exact warp-level fold from its exact entry value
-          float sq = sm_s;
+          float sq = __fmul_rn(__uint2float_rn(m_prev), b.u);
           bool hq = true;
           for (int c = 0; c < CH; c++) {
             float v[8];
@@ -1161,20 +1194,18 @@ __global__ void __launch_bounds__(GM_TMA_W * 32)
             load(c, v, vmask);
             fx::warp_fold(v, vmask, sq, hq, lane);
           }
-          if (lane == 0) sm_s = sq;
+          if (lane == 0) sm_s[g2] = sq;
         }
-        first = f + 1;
         __syncthreads();
+        s = sm_s[g2];
+        gen++;
+        first = f + 1;
       }
-      __syncthreads();  // round done: its buffer may be refilled, sm_s is final for the round
     }
     if constexpr (EPI) {
-      if (threadIdx.x == 0) {
-        const float res = sm_s;
-        if (fused_apply_send<P, T, float, V>(pb, ep, vtx, sm_have != 0, res)) raise_flag(ep.flag);
-      }
-    } else if (threadIdx.x == 0 && sm_have) {
-      y[vtx] = sm_s;
+      if (threadIdx.x == 0 && fused_apply_send<P, T, float, V>(pb, ep, vtx, have, s)) raise_flag(ep.flag);
+    } else if (threadIdx.x == 0 && have) {
+      y[vtx] = s;
       atomicOr(ybits + (vtx >> 5), 1u << (vtx & 31));
     }
   }
@@ -1524,7 +1555,7 @@ struct engine {
         static const bool no_stage = getenv("GM_NO_STAGE") != nullptr;
         if (M.n_long > 0 && !no_stage) {
           void* scratch = nullptr;
-          if (gm_vectors_scratch(vecs, (M.long_entries + 64 + 2 * GM_TMA_ROUND) * (long long)sizeof(T), &scratch)) return 1;
+          if (gm_vectors_scratch(vecs, (M.long_entries + 64 + (GM_TMA_BUFS + 1) * GM_TMA_ROUND) * (long long)sizeof(T), &scratch)) return 1;
           T* staged = (T*)scratch;
           const long long groups = (M.long_entries + 7) / 8;
           k_stage_rows<T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(M.h_col, M.long_entries, x, hot, staged);
@@ -1533,7 +1564,7 @@ struct engine {
             *staged_recorded = true;
           }
           auto kt = k_heavy_fadd32_tma<P, T, V, IDENT, EPI>;
-          constexpr int ring_bytes = 2 * GM_TMA_ROUND * 4;
+          constexpr int ring_bytes = GM_TMA_BUFS * GM_TMA_ROUND * 4;
           static bool attr = false;
           if (!attr) {
             GM_CUDA_OK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));

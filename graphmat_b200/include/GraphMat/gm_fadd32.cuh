@@ -99,6 +99,23 @@ GM_HD inline qmap quantize(float a, const binade& b, bool& bad) {
   return q;
 }
 
+#if defined(__CUDACC__)
+// q0 alone, and whether the addend is a TIE.  a/u is exact (a power-of-two scaling), q0 = RN_even(a/u) is what
+// fl(B0 + a) computes (B0's integer 2^23 is even), and q1 differs from q0 only when a/u lies exactly half way
+// between two integers (then the odd neighbour is taken).  Without ties a run of addends is the plain translation
+// m -> m + sum(q0): no (q0, q1) pairs, no parity selects.
+__device__ __forceinline__ unsigned quantize_q0(float a, const binade& b, bool& bad, bool& tie) {
+  if (!(a >= 0.0f && a < b.B0)) {  // negative, NaN, or certain to leave the binade
+    bad = true;
+    return 0u;
+  }
+  const float t = __fmul_rn(a, b.inv_u);
+  const float r = rintf(t);  // round half to even
+  tie |= fabsf(__fsub_rn(t, r)) == 0.5f;
+  return (unsigned)__float2int_rn(r);
+}
+#endif
+
 // plain serial fold of up to 8 addends held by one lane; bit k of vmask = addend k exists
 GM_HD inline void serial8(const float (&v)[kPerLane], unsigned vmask, float& s, bool& have) {
 #pragma unroll

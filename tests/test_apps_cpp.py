@@ -100,7 +100,7 @@ def test_apply_edges_cpp(n):
     """test/test_apply_edges.cpp of the reference (applyToAllEdges + getEdgelist) on the C++ mirror, and SSSP over
     the rewritten weights (the device matrices carry them)"""
     out = run("ApplyEdgesCheck", n)
-    assert "apply_edges ok" in out and "device functors ok" in out
+    assert "apply_edges ok" in out and "device functors ok" in out and "snapshot ok" in out
 
 
 @pytest.mark.parametrize("policy", ["default", "always_push", "never_push"])
