@@ -7,7 +7,9 @@
 
 #include "GraphMat/gm_engine.cuh"
 #include "GraphMat/programs/BFS.h"
+#include "GraphMat/gm_vertex_ops.cuh"
 #include "GraphMat/programs/IncrementalPageRank.h"
+#include "GraphMat/programs/LDA.h"
 #include "GraphMat/programs/TopologicalSort.h"
 #include "GraphMat/programs/PageRank.h"
 #include "GraphMat/programs/SGD.h"
@@ -83,6 +85,45 @@ template <> struct binder<TopSort> {
   static void out(const TopSort& p, void* s) { if (s) ((gm_topsort_state*)s)->current_topsort_order = p.current_topsort_order; }
 };
 
+// LDA, K = 20 (src/LDA.cpp:278): global_N is recomputed on the device through the functor reduce
+void lda_recalc20(void* ctx, LDAVector<20>* out) {
+  gm::map_reduce_vertices<LDAVector<20>, LDAVector<20> >((gm_graph*)ctx, out, LDAIfTerm<20>(), LDAAdd<20>());
+}
+template <> struct binder<LDAInitProgram<20> > {
+  static int bytes() { return 0; }
+  static void in(LDAInitProgram<20>&, const void*) {}
+  static void out(const LDAInitProgram<20>&, void*) {}
+};
+template <> struct binder<LDAProgram<20> > {
+  static int bytes() { return sizeof(gm_lda_state); }
+  static void in(LDAProgram<20>& p, const void* s) {
+    if (!s) return;
+    const gm_lda_state* t = (const gm_lda_state*)s;
+    p.alpha = t->alpha; p.eta = t->eta; p.vocab_size = t->vocab_size;
+    for (int i = 0; i < 20; i++) p.global_N.N[i] = t->global_N[i];
+  }
+  static void out(const LDAProgram<20>& p, void* s) {
+    if (s) for (int i = 0; i < 20; i++) ((gm_lda_state*)s)->global_N[i] = p.global_N.N[i];
+  }
+};
+template <> struct binder<LDALLProgram<20> > {
+  static int bytes() { return sizeof(gm_ldall_state); }
+  static void in(LDALLProgram<20>& p, const void* s) {
+    if (!s) return;
+    const gm_ldall_state* t = (const gm_ldall_state*)s;
+    p.eta = t->eta; p.nterms = t->nterms;
+    for (int i = 0; i < 20; i++) p.N_k.N[i] = t->N_k[i] + t->nterms * (t->eta - 1.0);  // the constructor's smoothing, :209-212
+  }
+  static void out(const LDALLProgram<20>&, void*) {}
+};
+// programs that need the graph itself on the host side (LDAProgram's do_every_iteration reduces over all vertices)
+template <class P> void bind_graph(P&, gm_graph*) {}
+template <> void bind_graph<LDAProgram<20> >(LDAProgram<20>& p, gm_graph* g) {
+  p.recalc = lda_recalc20;
+  p.recalc_ctx = g;
+  p.calcGlobalN();  // ldap.calcGlobalN() right after construction, src/LDA.cpp:300
+}
+
 enum { OP_RUN, OP_SEND, OP_SPMSPV, OP_APPLY, OP_SIZES };
 struct call {
   int op;
@@ -108,6 +149,7 @@ int dispatch(const call& c) {
   P prog;
   binder<P>::in(prog, c.state);
   if (c.op == OP_RUN) {
+    bind_graph(prog, c.g);
     int rc = EN::run(prog, c.g, c.iterations, c.tmp, c.stats);
     binder<P>::out(prog, c.state);
     return rc;
@@ -151,6 +193,9 @@ int route(int program, const call& c) {
     case GM_PROG_DELTAPAGERANK: return dispatch<DeltaPageRank>(c);
     case GM_PROG_INDEGREE: return dispatch<InDegree<TopSortVertex, int> >(c);
     case GM_PROG_TOPSORT: return dispatch<TopSort>(c);
+    case GM_PROG_LDAINIT20: return dispatch<LDAInitProgram<20> >(c);
+    case GM_PROG_LDA20: return dispatch<LDAProgram<20> >(c);
+    case GM_PROG_LDALL20: return dispatch<LDALLProgram<20> >(c);
   }
   gm_set_error("unknown program id");
   return 1;

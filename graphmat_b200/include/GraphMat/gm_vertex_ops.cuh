@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) k_map_vertices(V* __restrict__ vp, int n,
 // block tree over 256 mapped values; partial[b] per block, valid[b] = the block saw at least one vertex
 template <class V, class T, class M, class R>
 __global__ void __launch_bounds__(256) k_map_reduce(V* __restrict__ vp, int n, M map, R reduce, T* __restrict__ partial) {
-  __shared__ T sm[256];
+  __shared__ __align__(16) unsigned char sm_raw[256 * sizeof(T)];  // raw storage: T may have a constructor
+  T* sm = reinterpret_cast<T*>(sm_raw);
   __shared__ unsigned char have[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   have[threadIdx.x] = i < n;
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(256) k_map_reduce(V* __restrict__ vp, int n, M
 }
 template <class T, class R>
 __global__ void __launch_bounds__(256) k_reduce_partials(const T* __restrict__ in, int n, R reduce, T* __restrict__ out) {
-  __shared__ T sm[256];
+  __shared__ __align__(16) unsigned char sm_raw[256 * sizeof(T)];
+  T* sm = reinterpret_cast<T*>(sm_raw);
   __shared__ unsigned char have[256];
   T acc;
   bool h = false;

@@ -259,8 +259,14 @@ enum {
   GM_PROG_DEGREE_DPR = 12,     /* src/IncrementalPageRank.cpp:53-78  V = dPR              */
   GM_PROG_DELTAPAGERANK = 13,  /* src/IncrementalPageRank.cpp:80-123 V = dPR              */
   GM_PROG_INDEGREE = 14,       /* src/TopologicalSort.cpp:60-87      V = Vertex_type      */
-  GM_PROG_TOPSORT = 15         /* src/TopologicalSort.cpp:90-130     V = Vertex_type      */
+  GM_PROG_TOPSORT = 15,        /* src/TopologicalSort.cpp:90-130     V = Vertex_type      */
+  GM_PROG_LDAINIT20 = 16,      /* src/LDA.cpp:69-111  K = 20         V = LatentVector<20> (the LDA one) */
+  GM_PROG_LDA20 = 17,          /* src/LDA.cpp:127-196: global_N is recomputed on the device before the run and in
+                                  every do_every_iteration, and handed back in the state */
+  GM_PROG_LDALL20 = 18         /* src/LDA.cpp:198-250 */
 };
+typedef struct gm_lda_state { double alpha, eta, vocab_size; double global_N[20]; } gm_lda_state;   /* src/LDA.cpp:129-132 */
+typedef struct gm_ldall_state { double N_k[20]; double eta; int nterms; } gm_ldall_state;          /* :201-203, N_k unsmoothed */
 typedef struct gm_deltapagerank_state { double alpha; int iter; } gm_deltapagerank_state; /* src/IncrementalPageRank.cpp:82-83 */
 typedef struct gm_topsort_state { unsigned int current_topsort_order; } gm_topsort_state;   /* src/TopologicalSort.cpp:93 */
 typedef struct gm_pagerank_state { float alpha; } gm_pagerank_state;                  /* src/PageRank.cpp:84 */
@@ -279,7 +285,8 @@ int gm_step_apply(gm_graph* g, int program, void* state, gm_vectors* tmp, int* c
 /* GM_REDUCE_REACHABLE also serves src/TopologicalSort.cpp:132-138 ("unreachable" = nvertices - reachable) */
 enum { GM_REDUCE_REACHABLE = 1,      /* src/BFS.cpp:101-108 etc.: count of vertices whose first uint field < UINT_MAX */
        GM_REDUCE_BUCKET_NOT_EMPTY = 2, /* src/DeltaStepping.cpp:109-111, param = bid */
-       GM_REDUCE_SQERR = 3 };        /* src/SGD.cpp:158-161: sum of the trailing double (sqerr) */
+       GM_REDUCE_SQERR = 3 };        /* src/SGD.cpp:158-161: sum of the trailing double (sqerr); also src/LDA.cpp:268-271,
+                                        338-339 (token_loglik is LatentVector's trailing double) */
 int gm_graph_reduce(const gm_graph* g, int what, int param, double* result);
 
 /* ---- test hooks: the bit-exact parallel fp32 fold used for long PageRank rows (gm_fadd32.cuh).
