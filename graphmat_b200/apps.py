@@ -163,3 +163,28 @@ def topsort(n, src, dst, val=None, threads=4, **kw):
     unreachable = G.nvertices - int(G.reduce(gm.REDUCE_REACHABLE))   # :132-138, 177-178
     out = G.get_vertexproperties()
     return out["topsort_order"].copy(), out["in_degree"].copy(), st.iterations, unreachable
+
+
+def lda(ndoc, nterms, src, dst, val, iterations=10, alpha=1.0, eta=5.0, threads=4, **kw):
+    """src/LDA.cpp:274-341 (K = 20) -> (N f64[ndoc+nterms, 20], global_N f64[20], total log-likelihood)"""
+    nv = ndoc + nterms
+    G = gm.Graph.from_edges(nv, src, dst, val, gm.LDA_DTYPE, threads=threads, **kw)
+    vp = np.zeros(nv, gm.LDA_DTYPE)
+    vp["type"][:ndoc] = b"d"                                       # :285-293
+    vp["type"][ndoc:] = b"w"
+    G.set_vertexproperties(vp)
+    G.set_all_active()
+    G.run(gm.PROG_LDAINIT20, None, 1)                              # :296-298
+    state = gm.LDAState(alpha, eta, float(nterms))
+    G.set_all_active()
+    G.run(gm.PROG_LDA20, state, iterations)                        # :300-313 (calcGlobalN before the run and per iteration)
+    gN = np.array(state.global_N[:], np.float64)
+    ll = gm.LDALLState()
+    for i in range(20):
+        ll.N_k[i] = gN[i]
+    ll.eta, ll.nterms = eta, nterms
+    G.set_all_active()
+    G.run(gm.PROG_LDALL20, ll, 1)                                  # :335-337
+    total = G.reduce(gm.REDUCE_SQERR)                              # sum of the trailing double = token_loglik, :338-339
+    out = G.get_vertexproperties()
+    return out["N"].copy(), gN, float(total)

@@ -20,6 +20,7 @@ UNTIL_CONVERGENCE = -1
 PROG_DEGREE, PROG_PAGERANK, PROG_BFS, PROG_SSSP, PROG_DELTASTEPPING = 1, 2, 3, 4, 5
 PROG_SGD20, PROG_RMSE20, PROG_SGD32, PROG_RMSE32, PROG_SGD4, PROG_RMSE4 = 6, 7, 8, 9, 10, 11
 PROG_DEGREE_DPR, PROG_DELTAPAGERANK, PROG_INDEGREE, PROG_TOPSORT = 12, 13, 14, 15
+PROG_LDAINIT20, PROG_LDA20, PROG_LDALL20 = 16, 17, 18
 REDUCE_REACHABLE, REDUCE_BUCKET_NOT_EMPTY, REDUCE_SQERR = 1, 2, 3
 SGD_PROGRAMS = {20: (PROG_SGD20, PROG_RMSE20), 32: (PROG_SGD32, PROG_RMSE32), 4: (PROG_SGD4, PROG_RMSE4)}
 
@@ -30,6 +31,8 @@ SSSP_DTYPE = np.dtype([("distance", np.uint32)])
 DS_DTYPE = np.dtype([("distance", np.uint32), ("bucket", np.int32)])
 DPR_DTYPE = np.dtype([("delta", np.float64), ("pagerank", np.float64), ("degree", np.int32)], align=True)
 TOPSORT_DTYPE = np.dtype([("topsort_order", np.uint32), ("in_degree", np.int32)])
+LDA_DTYPE = np.dtype({"names": ["N", "type", "token_loglik"], "formats": [(np.float64, (20,)), "S1", np.float64],
+                      "offsets": [0, 160, 168], "itemsize": 176})  # LatentVector<20> of src/LDA.cpp:36-47
 
 
 def latent_dtype(K):
@@ -103,6 +106,14 @@ class DeltaPageRankState(C.Structure):
 
 class TopSortState(C.Structure):
     _fields_ = [("current_topsort_order", C.c_uint)]
+
+
+class LDAState(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("eta", C.c_double), ("vocab_size", C.c_double), ("global_N", C.c_double * 20)]
+
+
+class LDALLState(C.Structure):
+    _fields_ = [("N_k", C.c_double * 20), ("eta", C.c_double), ("nterms", C.c_int)]
 
 
 class SGDState(C.Structure):

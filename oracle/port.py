@@ -107,6 +107,18 @@ def topsort(n, src, dst, val=None, threads=4):
     return order, indeg, it, un.value
 
 
+def lda(ndoc, nterms, src, dst, val, iterations=10, alpha=1.0, eta=5.0, threads=4):
+    """src/LDA.cpp:274-341 (K = 20) -> (N f64[ndoc+nterms, 20], global_N f64[20], total log-likelihood)"""
+    src, dst, val = _i32(src), _i32(dst), _i32(val)
+    n = ndoc + nterms
+    N = np.empty((n, 20), np.float64)
+    gN = np.empty(20, np.float64)
+    ll = C.c_double()
+    lib().gmo_lda(C.c_int(threads), C.c_int(ndoc), C.c_int(nterms), C.c_int(len(src)), _p(src), _p(dst), _p(val),
+                  C.c_int(iterations), C.c_double(alpha), C.c_double(eta), _p(N), _p(gN), C.byref(ll))
+    return N, gN, ll.value
+
+
 def rowblock_sum_f32(n, src, dst, row_begin, row_end, x, xbit, y, ybit, threads=4):
     src, dst = _i32(src), _i32(dst)
     lib().gmo_rowblock_sum_f32(C.c_int(threads), C.c_int(n), C.c_int(len(src)), _p(src), _p(dst), C.c_int(row_begin),

@@ -156,6 +156,18 @@ def topsort(n, src, dst, val=None, threads=4):
     return order, indeg, it, un.value, ms.value
 
 
+def lda(ndoc, nterms, src, dst, val, iterations=10, alpha=1.0, eta=5.0, threads=4):
+    """-> (N f64[ndoc+nterms, 20], global_N f64[20], total log-likelihood, ms)."""
+    src, dst, val = _i32(src), _i32(dst), _i32(val)
+    n = ndoc + nterms
+    N = np.empty((n, 20), np.float64)
+    gN = np.empty(20, np.float64)
+    ll, ms = C.c_double(), C.c_double()
+    _lib("lda").gm_ref_lda(C.c_int(threads), C.c_int(ndoc), C.c_int(nterms), C.c_int(len(src)), _p(src), _p(dst), _p(val),
+                           C.c_int(iterations), C.c_double(alpha), C.c_double(eta), _p(N), _p(gN), C.byref(ll), C.byref(ms))
+    return N, gN, ll.value, ms.value
+
+
 class PageRankSession:
     """Build once, time run_graph_program per call (bench.py reference arm / cpu_baseline)."""
 

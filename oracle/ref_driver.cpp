@@ -36,6 +36,8 @@
 #include "src/IncrementalPageRank.cpp"
 #elif defined(GM_REF_APP_TOPOLOGICALSORT)
 #include "src/TopologicalSort.cpp"
+#elif defined(GM_REF_APP_LDA)
+#include "src/LDA.cpp"
 #else
 #error "pick one reference app"
 #endif
@@ -376,6 +378,50 @@ int gm_ref_topsort(int threads, int m, int n, int nnz, const int* src, const int
     in_degree[i - 1] = p.in_degree;
   }
   return (int)topsort.current_topsort_order - 1;
+}
+#endif
+
+#if defined(GM_REF_APP_LDA)
+// run_lda, /root/reference/src/LDA.cpp:274-341 (K = 20 there).  The app's LatentVector leaves N[] uninitialised
+// (:44-46) and then reads it from vertices that never receive a message; the vertices are created zeroed here.
+int gm_ref_lda(int threads, int ndoc, int nterms, int nnz, const int* src, const int* dst, const int* val, int iterations,
+               double alpha, double eta, double* N_out, double* global_N_out, double* total_ll, double* ms) {
+  Quiet q;
+  omp_set_num_threads(threads);
+  const int k = 20;
+  const int n = ndoc + nterms;
+  GraphMat::Graph<LatentVector<k> > G;
+  ingest(G, n, n, nnz, src, dst, val, true);
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    LatentVector<k> v;
+    memset((void*)&v, 0, sizeof v);
+    v.type = i <= ndoc ? 'd' : 'w';
+    G.setVertexproperty(i, v);
+  }
+  LDAInitProgram<k> ldainit_program;
+  G.setAllActive();
+  GraphMat::run_graph_program(&ldainit_program, G, 1);
+  LDAProgram<k> ldap(G, alpha, eta, nterms);
+  ldap.calcGlobalN();
+  auto ldap_tmp = GraphMat::graph_program_init(ldap, G);
+  double t0 = now_ms();
+  G.setAllActive();
+  GraphMat::run_graph_program(&ldap, G, iterations, &ldap_tmp);
+  if (ms) *ms = now_ms() - t0;
+  GraphMat::graph_program_clear(ldap_tmp);
+  auto Nk = ldap.global_N;
+  for (int j = 0; j < k; j++) global_N_out[j] = Nk.N[j];
+  LDALLProgram<k> ldall(Nk, eta, nterms);
+  G.setAllActive();
+  GraphMat::run_graph_program(&ldall, G, 1);
+  double tot = 0.0;
+  G.applyReduceAllVertices(&tot, return_ll<k>);
+  *total_ll = tot;
+  for (int i = 1; i <= G.getNumberOfVertices(); i++) {
+    LatentVector<k> p = G.getVertexproperty(i);
+    for (int j = 0; j < k; j++) N_out[(size_t)(i - 1) * k + j] = p.N[j];
+  }
+  return iterations;
 }
 #endif
 

@@ -86,6 +86,10 @@ def main():
              ts_unreachable=unreach, dag_order=dorder, dag_in_degree=dindeg, dag_iterations=dtit, dag_unreachable=dun,
              mtx_dpr_pagerank=mpr, mtx_dpr_delta=mdelta, mtx_dpr_degree=mdeg, mtx_dpr_iterations=mit,
              mtx_ts_order=morder, mtx_ts_in_degree=mindeg, mtx_ts_iterations=mtit, mtx_ts_unreachable=mun)
+    # --- LDA (K = 20): seeded document-term counts ---
+    dd, tt, cc = util.doc_term_counts(300, 120, 4000)
+    N, gN, ll, _ = ref.lda(300, 120, dd, tt, cc, iterations=10, threads=4)
+    save("lda_t4", threads=4, N=N, global_N=gN, loglik=ll)
 
 
 if __name__ == "__main__":

@@ -133,3 +133,17 @@ def test_f3_apps_on_fixtures(tmp_path):
     out = run("TopologicalSort", prefix, "--dump", d)
     a = np.loadtxt(d, dtype=np.int64)
     assert (a[:, 1] == g["dag_order"]).all() and "Top Sort order 1 :" in out
+
+
+def test_lda_app(tmp_path):
+    """LDA through the C++ mirror: do_every_iteration reduces over all vertices on the device (functor overload)"""
+    g = np.load(os.path.join(util.GOLDEN, "lda_t4.npz"))
+    dd, tt, cc = util.doc_term_counts(300, 120, 4000)
+    prefix = str(tmp_path / "docs.bin.mtx")
+    write_mtx(prefix, 420, 420, dd, tt, cc)
+    d = str(tmp_path / "dump.txt")
+    out = run("LDA", prefix, 300, 120, 10, "--dump", d)
+    a = np.loadtxt(d)[:, 1:]
+    assert np.max(np.abs(a - g["N"]) / np.maximum(np.abs(g["N"]), 1e-9)) <= 1e-6
+    ll = float(out.split("Total Loglikelihood =")[1].split()[0])
+    assert abs(ll - float(g["loglik"])) <= 1e-6 * abs(float(g["loglik"]))

@@ -464,3 +464,18 @@ def test_f3_programs_rmat18_vs_reference(monkeypatch):
     rorder, rindeg, rtit, run_, _ = ref.topsort(nd, ds_, dd_, None, threads=REF_THREADS)
     order, indeg, tit, un = apps.topsort(nd, ds_, dd_, None, threads=REF_THREADS)
     assert tit == rtit and un == run_ and (order == rorder).all() and (indeg == rindeg).all()
+
+
+def test_golden_lda_gpu():
+    """LDA (ALL_EDGES, 176-byte messages, rand_r inside process_message, global_N reduced on the device in every
+    do_every_iteration) against the golden output of the unmodified reference"""
+    g = load("lda_t4")
+    dd, tt, cc = util.doc_term_counts(300, 120, 4000)
+    N, gN, ll = apps.lda(300, 120, dd, tt, cc, iterations=10, threads=4)
+    assert_rel(N + 1e-9, g["N"] + 1e-9)
+    assert_rel(gN, g["global_N"])
+    assert abs(ll - float(g["loglik"])) <= 1e-6 * abs(float(g["loglik"]))
+    oN, ogN, oll = port.lda(300, 120, dd, tt, cc, iterations=3, threads=4)
+    N3, gN3, ll3 = apps.lda(300, 120, dd, tt, cc, iterations=3, threads=4, heavy_threshold=16)
+    assert_rel(N3 + 1e-9, oN + 1e-9)
+    assert abs(ll3 - oll) <= 1e-6 * abs(oll)

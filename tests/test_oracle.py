@@ -215,3 +215,15 @@ def test_oracle_generator_is_the_products_generator():
     a = ref.rmat_edges(14, 16, seed=1, weight_max=127, weight_seed=2)
     b = capi.rmat_edges(14, 16, seed=1, weight_max=127, weight_seed=2)
     assert a[0] == b[0] and all((x == y).all() for x, y in zip(a[1:], b[1:]))
+
+
+def test_golden_lda():
+    """LDA K = 20, 10 iterations: fp64, within north_star's 1e-6 of the unmodified reference (observed ~1e-15)"""
+    g = load("lda_t4")
+    dd, tt, cc = util.doc_term_counts(300, 120, 4000)
+    N, gN, ll = port.lda(300, 120, dd, tt, cc, iterations=10, threads=4)
+    np.testing.assert_allclose(N, g["N"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(gN, g["global_N"], rtol=1e-6)
+    assert abs(ll - float(g["loglik"])) <= 1e-6 * abs(float(g["loglik"]))
+    # conservation: every term count is spread over the 20 topics, once per endpoint
+    assert abs(N[:300].sum() - cc.sum()) < 1e-6 * cc.sum() and abs(N[300:].sum() - cc.sum()) < 1e-6 * cc.sum()

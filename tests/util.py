@@ -85,3 +85,13 @@ def random_dag(n, m, seed=1):
     v = rng.integers(1, n + 1, m)
     keep = u < v
     return n, u[keep].astype(np.int32), v[keep].astype(np.int32)
+
+
+def doc_term_counts(ndoc, nterms, nnz, seed=9):
+    """seeded bipartite document-term count graph for LDA (src/LDA.cpp): documents are ids 1..ndoc, terms
+    ndoc+1..ndoc+nterms, edge value = term count 1..9; every vertex gets at least one edge"""
+    rng = np.random.default_rng(seed)
+    d = np.concatenate([np.arange(1, ndoc + 1), rng.integers(1, ndoc + 1, nnz - ndoc)])
+    t = np.concatenate([rng.integers(1, nterms + 1, ndoc), np.arange(1, nterms + 1), rng.integers(1, nterms + 1, nnz - ndoc - nterms)])[:len(d)]
+    c = rng.integers(1, 10, len(d))
+    return d.astype(np.int32), (t + ndoc).astype(np.int32), c.astype(np.int32)
