@@ -1002,16 +1002,25 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
 // round by round.  Their gathers are already hoisted out (k_stage_rows); this kernel streams the dense staging
 // array with BULK ASYNC COPIES (cp.async.bulk, the TMA engine) into a double-buffered shared-memory ring, one
 // mbarrier per buffer, so the copy of round r+1 runs under the fold of round r and a round costs shared-memory
-// reads instead of an L2 round trip.  A round is GM_TMA_ROUND = 32 warps x 2 chunks x 256 addends; every warp
+// reads instead of an L2 round trip.  A round is GM_TMA_ROUND = 32 warps x GM_TMA_CH chunks x 256 addends; every warp
 // scans its chunks under the binade of the block's entry value and publishes ONE composed map; after a single
 // block barrier EVERY warp scans the 32 published maps itself and so knows the new running value (held in
 // registers by all threads) -- a round that stays inside its binade costs one barrier (k_heavy_fadd32: three, with
 // warp 0 scanning while the others wait).  Same addends, same order, same exactness argument as k_heavy_fadd32
 // (all q >= 0: the exit value decides).
 constexpr int GM_TMA_W = 32;                                   // warps per block
-constexpr int GM_TMA_CH = 2;                                   // 256-addend chunks per warp and round
-constexpr int GM_TMA_ROUND = GM_TMA_W * 256 * GM_TMA_CH;       // addends per round (16384 -> 64 KB per buffer)
-constexpr int GM_TMA_BUFS = 3;                                 // ring depth: two rounds in flight behind the one being folded
+#ifndef GM_TMA_CHUNKS
+#define GM_TMA_CHUNKS 1
+#endif
+#ifndef GM_TMA_NBUF
+#define GM_TMA_NBUF 2
+#endif
+constexpr int GM_TMA_CH = GM_TMA_CHUNKS;                       // 256-addend chunks per warp and round
+constexpr int GM_TMA_ROUND = GM_TMA_W * 256 * GM_TMA_CH;       // addends per round (8192 -> 32 KB per buffer)
+// The ring is kept SMALL (2 x 32 KB): the SMs that hosted a long-row block keep its shared-memory carve-out, and the
+// sliced-ELL blocks that follow there lose that much L1.  Measured, pass of rank 0 of 2 / 4 / 8 (176 / 88 / 44
+// long-row blocks): 3 x 64 KB 3.08 / - / 0.725 ms, 2 x 64 KB 2.28 / 1.22 / 0.70 ms, 2 x 32 KB 2.17 / 1.19 / 0.69 ms.
+constexpr int GM_TMA_BUFS = GM_TMA_NBUF;
 constexpr int GM_TMA_PARTS = 8;                                // bulk copies per round (8 KB each)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -1491,6 +1500,7 @@ struct step_counters {
   long long push_passes = 0;
   long long last_frontier_cols = -1, last_frontier_entries = -1;  // of the latest sparse pass (trace only)
   long long next_entries = -1;  // entries of the coming pass's frontier when k_apply counted them (-1: unknown)
+  bool last_pass_pushed = false;  // the latest SpMSpV pass took the sparse-frontier path (y is sparse)
   bool ybits_clean = false;     // k_send already cleared y's bit words for the coming pass
   bool counted_by_kernel = false;  // gm_push_count ran in this iteration (its scratch words overlap k_apply's counter)
 };
@@ -1521,7 +1531,10 @@ struct engine {
     const int n = gv.n_local_pad;
     T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
     unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
-    if (prog.getActivity() != GraphMat::ALL_VERTICES) {
+    // ACTIVE_ONLY programs sweep the bit words unless the frontier is known to be dense (k_apply counted its entries):
+    // a dense sweep is faster one thread per vertex
+    const bool dense_frontier = sc && sc->next_entries >= 0 && sc->next_entries * 8 > gv.nnz;
+    if (prog.getActivity() != GraphMat::ALL_VERTICES && !dense_frontier) {
       const int nw = n >> 5;
       k_send_words<P, T, V><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(pack(prog), nw, (const V*)gv.vertexproperty, gv.active_bits,
                                                                       xloc, xb, sc ? vv.y_bits : nullptr);
@@ -1659,7 +1672,7 @@ struct engine {
         if (sc) { sc->last_frontier_cols = n_act; sc->last_frontier_entries = n_ent; }
         if (n_ent * push_div <= M.nnz) {
           if (n_ent == 0) {  // nothing arrives: y stays cleared
-            if (sc) sc->push_passes++;
+            if (sc) { sc->push_passes++; sc->last_pass_pushed = true; }
             return 0;
           }
           gm_graph_view gv2;
@@ -1685,7 +1698,7 @@ struct engine {
               k_push_atomic<P, T, U, V, E, NEEDVP, IDENT, 2><<<blocks, 256, 0, st>>>(pb, MP, n_words, wblocks, vv.x_bits, x, vp, y, vv.y_bits, nullptr);
               if (sc) sc->launches += 1;
             }
-            if (sc) { sc->edges += n_ent; sc->push_passes++; }
+            if (sc) { sc->edges += n_ent; sc->push_passes++; sc->last_pass_pushed = true; }
             GM_CUDA_OK(cudaGetLastError());
             return 0;
           }
@@ -1696,7 +1709,7 @@ struct engine {
               if (sc) sc->counted_by_kernel = true;
             }
             if (n_ent == 0) {
-              if (sc) sc->push_passes++;
+              if (sc) { sc->push_passes++; sc->last_pass_pushed = true; }
               return 0;
             }
             gm_push_plan plan;
@@ -1716,7 +1729,7 @@ struct engine {
             if (big_smem(kfl, 4 * 32 * sizeof(U))) return 1;
             kfl<<<lb, 128, 4 * 32 * sizeof(U), st>>>(pb, MP, n_long, long_runs, plan.keys, plan.order, (const U*)plan.vals, y,
                                                      vv.y_bits);
-            if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; }
+            if (sc) { sc->launches += 5; sc->edges += n_ent; sc->push_passes++; sc->last_pass_pushed = true; }
             GM_CUDA_OK(cudaGetLastError());
             return 0;
           }
@@ -1789,7 +1802,7 @@ struct engine {
         GM_CUDA_OK(cudaEventRecord(joins[k], aux[k]));
         GM_CUDA_OK(cudaStreamWaitEvent(st, joins[k], 0));
       }
-    if (sc) sc->edges += M.nnz;
+    if (sc) { sc->edges += M.nnz; sc->last_pass_pushed = false; }
     GM_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -1877,7 +1890,10 @@ struct engine {
       unsigned long long* next = reinterpret_cast<unsigned long long*>(gv.d_flags + 10);
       if (c_ptr && (!sc || sc->counted_by_kernel)) GM_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
       if (sc) sc->counted_by_kernel = false;
-      if (prog.getActivity() != GraphMat::ALL_VERTICES) {
+      // after a row-major (dense) pass most vertices hold a message: one thread per vertex; after a sparse-frontier
+      // pass: the word sweep
+      const bool dense_y = sc && !sc->last_pass_pushed;
+      if (prog.getActivity() != GraphMat::ALL_VERTICES && !dense_y) {
         const int nw = n >> 5;
         k_apply_words<P, T, U, V, RESET><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(
             pack(prog), nw, (U*)vv.y_val, vv.y_bits, (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, c_ptr, next, gv.rank * n);
