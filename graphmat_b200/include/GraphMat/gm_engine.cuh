@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
   }
   bool any = false;
   unsigned long long ents = 0;
+  int n_changed = 0;  // warp-uniform
 #pragma unroll
   for (int k = 0; k < VPT; k++) {
     const int i = base + k * 256;
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
       x[i] = t;
     }
     const unsigned m = __ballot_sync(0xffffffffu, changed);
+    n_changed += __popc(m);
     if ((threadIdx.x & 31) == 0 && i < n_pad) {
       if (FUSE) {
         const unsigned all = i + 32 <= n_valid ? 0xffffffffu : (i < n_valid ? (1u << (n_valid - i)) - 1u : 0u);
@@ -316,7 +318,10 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
   if (any && *((volatile int*)flags) == 0) atomicExch(flags, 1);
   if (!FUSE && c_ptr) {
     for (int o = 16; o; o >>= 1) ents += __shfl_down_sync(0xffffffffu, ents, o);
-    if ((threadIdx.x & 31) == 0 && ents) atomicAdd(next_entries, ents);
+    if ((threadIdx.x & 31) == 0 && n_changed) {
+      atomicAdd(next_entries, ents);
+      atomicAdd(next_entries - 1, (unsigned long long)n_changed);
+    }
   }
 }
 
@@ -395,8 +400,15 @@ __global__ void __launch_bounds__(256) k_apply_words(prog_bytes<P> pb, int n_wor
   if (w < n_words) active[w] = out;  // setAllInactive + set where changed
   if (__ballot_sync(0xffffffffu, out != 0) != 0 && lane == 0) raise_flag(flags);
   if (c_ptr) {
-    for (int o = 16; o; o >>= 1) ents += __shfl_down_sync(0xffffffffu, ents, o);
-    if (lane == 0 && ents) atomicAdd(next_entries, ents);
+    unsigned long long verts = __popc(out);
+    for (int o = 16; o; o >>= 1) {
+      ents += __shfl_down_sync(0xffffffffu, ents, o);
+      verts += __shfl_down_sync(0xffffffffu, verts, o);
+    }
+    if (lane == 0 && verts) {
+      atomicAdd(next_entries, ents);
+      atomicAdd(next_entries - 1, verts);  // [-1]: vertices of the next frontier, [0]: entries of their columns
+    }
   }
 }
 
@@ -1500,6 +1512,7 @@ struct step_counters {
   long long push_passes = 0;
   long long last_frontier_cols = -1, last_frontier_entries = -1;  // of the latest sparse pass (trace only)
   long long next_entries = -1;  // entries of the coming pass's frontier when k_apply counted them (-1: unknown)
+  long long next_vertices = -1; // ... and its vertices
   bool last_pass_pushed = false;  // the latest SpMSpV pass took the sparse-frontier path (y is sparse)
   bool ybits_clean = false;     // k_send already cleared y's bit words for the coming pass
   bool counted_by_kernel = false;  // gm_push_count ran in this iteration (its scratch words overlap k_apply's counter)
@@ -1531,10 +1544,9 @@ struct engine {
     const int n = gv.n_local_pad;
     T* xloc = reinterpret_cast<T*>(vv.x_val) + (size_t)gv.rank * n;
     unsigned* xb = vv.x_bits + (size_t)gv.rank * (n >> 5);
-    // ACTIVE_ONLY programs sweep the bit words unless the frontier is known to be dense (k_apply counted its entries):
-    // a dense sweep is faster one thread per vertex
-    const bool dense_frontier = sc && sc->next_entries >= 0 && sc->next_entries * 8 > gv.nnz;
-    if (prog.getActivity() != GraphMat::ALL_VERTICES && !dense_frontier) {
+    // ACTIVE_ONLY programs sweep the bit words.  (Switching to one thread per vertex for dense frontiers / after
+    // row-major passes was measured: BFS RMAT-22 0.885 -> 0.85 ms, but RMAT-26 4.22 -> 5.25 ms; not kept.)
+    if (prog.getActivity() != GraphMat::ALL_VERTICES) {
       const int nw = n >> 5;
       k_send_words<P, T, V><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(pack(prog), nw, (const V*)gv.vertexproperty, gv.active_bits,
                                                                       xloc, xb, sc ? vv.y_bits : nullptr);
@@ -1888,12 +1900,9 @@ struct engine {
       if (count_next && gv.world == 1 && order != GraphMat::ALL_EDGES)
         c_ptr = order == GraphMat::OUT_EDGES ? gv.AT.c_ptr : gv.A.c_ptr;
       unsigned long long* next = reinterpret_cast<unsigned long long*>(gv.d_flags + 10);
-      if (c_ptr && (!sc || sc->counted_by_kernel)) GM_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+      if (c_ptr && (!sc || sc->counted_by_kernel)) GM_CUDA_OK(cudaMemsetAsync(next - 1, 0, 2 * sizeof(unsigned long long), st));
       if (sc) sc->counted_by_kernel = false;
-      // after a row-major (dense) pass most vertices hold a message: one thread per vertex; after a sparse-frontier
-      // pass: the word sweep
-      const bool dense_y = sc && !sc->last_pass_pushed;
-      if (prog.getActivity() != GraphMat::ALL_VERTICES && !dense_y) {
+      if (prog.getActivity() != GraphMat::ALL_VERTICES) {
         const int nw = n >> 5;
         k_apply_words<P, T, U, V, RESET><<<((nw + 31) / 32 + 7) / 8, 256, 0, st>>>(
             pack(prog), nw, (U*)vv.y_val, vv.y_bits, (V*)gv.vertexproperty, gv.active_bits, gv.d_flags, c_ptr, next, gv.rank * n);
@@ -2074,6 +2083,7 @@ struct engine {
         GM_CUDA_OK(cudaStreamSynchronize(st));
         int changed = gv.h_flags[0];
         sc.next_entries = counted ? (long long)*reinterpret_cast<unsigned long long*>(gv.h_flags + 10) : -1;
+        sc.next_vertices = counted ? (long long)*reinterpret_cast<unsigned long long*>(gv.h_flags + 8) : -1;
         if (gv.world > 1 && !peers && gm_graph_allreduce_or(g, &changed)) return 1;
         converged = !changed;
         if (timing) {
