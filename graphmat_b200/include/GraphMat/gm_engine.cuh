@@ -1787,7 +1787,8 @@ struct engine {
       static const int spw_tail = getenv("GM_SELL_SPW") ? atoi(getenv("GM_SELL_SPW")) : 8;
       const int nw = M.n_slices_wide < M.n_slices ? M.n_slices_wide : M.n_slices;
       constexpr bool LASTW = is_last_writer<P>::value && !ALLACT && sizeof(T) <= 8 && sizeof(U) <= 8;
-      if (nw > 0) {
+      auto launch_wide = [&]() -> int {
+        if (nw <= 0) return 0;
         if constexpr (LASTW)
           k_sell_last<P, T, U, V, E, NEEDVP, IDENT, ACCUM, 8><<<(nw + 7) / 8, 256, 0, st>>>(
               pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits);
@@ -1795,8 +1796,10 @@ struct engine {
           k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UW, EPI><<<(nw + 7) / 8, 256, 0, st>>>(
               pb, M, 0, nw, 1, hot, x, vv.x_bits, vp, y, vv.y_bits, ep);
         if (sc) sc->launches++;
-      }
-      if (M.n_slices > nw) {
+        return 0;
+      };
+      auto launch_tail = [&]() -> int {
+        if (M.n_slices <= nw) return 0;
         const int warps = (M.n_slices - nw + spw_tail - 1) / spw_tail;
         cudaStream_t ts = (nw > 0 && aux[2]) ? on_aux(2) : st;  // the narrow tail beside the wide slices
         if (enter(ts)) return 1;
@@ -1807,6 +1810,17 @@ struct engine {
           k_sell<P, T, U, V, E, ALLACT, NEEDVP, IDENT, ACCUM, UN, EPI><<<(warps + 7) / 8, 256, 0, ts>>>(
               pb, M, nw, M.n_slices, spw_tail, hot, x, vv.x_bits, vp, y, vv.y_bits, ep);
         if (sc) sc->launches++;
+        return 0;
+      };
+      // The narrow tail holds most of the ROWS, i.e. most of the messages the fused epilogue stores into the peers.
+      // Last in the pass, those stores bunch up behind it (8 GPUs: 224 MB per rank in the final ~0.15 ms, more than
+      // NVLink takes); first, they travel under the wide slices.
+      static const bool tail_first_env = getenv("GM_TAIL_FIRST") ? atoi(getenv("GM_TAIL_FIRST")) != 0 : true;
+      const bool tail_first = EPI && ep.n_peers > 0 && tail_first_env;
+      if (tail_first) {
+        if (launch_tail() || launch_wide()) return 1;
+      } else {
+        if (launch_wide() || launch_tail()) return 1;
       }
     }
     for (int k = 0; k < 3; k++)
