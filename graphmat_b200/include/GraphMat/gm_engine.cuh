@@ -1814,9 +1814,11 @@ struct engine {
       };
       // The narrow tail holds most of the ROWS, i.e. most of the messages the fused epilogue stores into the peers.
       // Last in the pass, those stores bunch up behind it (8 GPUs: 224 MB per rank in the final ~0.15 ms, more than
-      // NVLink takes); first, they travel under the wide slices.
-      static const bool tail_first_env = getenv("GM_TAIL_FIRST") ? atoi(getenv("GM_TAIL_FIRST")) != 0 : true;
-      const bool tail_first = EPI && ep.n_peers > 0 && tail_first_env;
+      // NVLink takes); first, they travel under the wide slices.  Measured: 8 GPUs 1179 -> 1247 GTEPS, 4 GPUs 694 -> 786,
+      // but 2 GPUs 461 -> 417 (one peer: the stores are no bottleneck and the wide slices lose their head start), so
+      // from four ranks on.
+      static const int tail_first_env = getenv("GM_TAIL_FIRST") ? atoi(getenv("GM_TAIL_FIRST")) : -1;
+      const bool tail_first = EPI && (tail_first_env < 0 ? ep.n_peers >= 3 : (tail_first_env != 0 && ep.n_peers > 0));
       if (tail_first) {
         if (launch_tail() || launch_wide()) return 1;
       } else {
