@@ -191,8 +191,8 @@ def pick_cpu_scale(target, budget_s, runs, iters, cores, forced=0):
     for sc in range(probe + 1, target + 1):
         f = 2.08 ** (sc - probe)
         e = build * f + runs * ms * 1e-3 * f
-        need_gb = (16 << sc) * 120 / 1e9  # edge list + both DCSC matrices + ingest copies: ~120 B per edge
-        if e > budget_s or need_gb > 0.6 * mem:
+        need_gb = (16 << sc) * 100 / 1e9  # edge list + both DCSC matrices + ingest copies: 99 B per edge measured (peak RSS)
+        if e > budget_s or need_gb > 0.7 * mem:
             break
         pick, est = sc, e
     why = ("largest scale whose build + %d steps fit %.0f s on %d cores (scale-%d probe: build %.1f s, step %.0f ms; "
@@ -258,7 +258,7 @@ def run_reference(args):
     cpu_env()
     from oracle import ref
     cores = os.cpu_count() or 1
-    budget = args.cpu_budget_s or 150.0
+    budget = args.cpu_budget_s or 240.0  # full scale-26 fits on this pool's hosts (16 cores, 196 GB): ~105 s build + 5.6 s per step
     warm = args.warmup
     if args.workload == "pagerank":
         scale, why = pick_cpu_scale(args.scale, budget, warm + args.steps, args.iters, cores, args.cpu_scale)
