@@ -608,10 +608,9 @@ static int graph_common_alloc(gm_graph* g) {
   CK(cudaEventCreateWithFlags(&g->ev_join2, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g->ev_join3, cudaEventDisableTiming));
   {
-    // One auxiliary stream by default.  Two or three (warp-per-row heavy rows / the narrow tail on streams of
-    // their own) measured no faster (rank 0 of 8: 0.875 vs 0.812 ms per pass, 1 GPU: 3.78 vs 3.78) and, with the
-    // fused epilogue, NOT bit-identical from the second iteration on (profiles/r2_multistream_rejected.txt):
-    // kept behind GM_AUX_STREAMS for experiments only.
+    // One auxiliary stream by default: two or three (warp-per-row heavy rows / the narrow tail on streams of their
+    // own, GM_AUX_STREAMS) measured no faster -- rank 0 of 8: 0.875 vs 0.812 ms per pass, 1 GPU: 3.78 vs 3.78
+    // (profiles/r2_multistream_rejected.txt, which also records the kernel race those experiments uncovered).
     int n_aux = 1;
     if (const char* e = getenv("GM_AUX_STREAMS")) n_aux = atoi(e);
     if (getenv("GM_NO_AUX_STREAM")) n_aux = 0;

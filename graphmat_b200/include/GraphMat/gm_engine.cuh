@@ -934,7 +934,11 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32)
           fx::binade b;
           const bool hot = have && fx::binade_of(s, b);  // block-uniform
           if (!hot) {
-            // no usable accumulator yet: warp `first` folds its 256 alone (exact for any input)
+            // no usable accumulator yet: warp `first` folds its 256 alone (exact for any input).  It publishes the
+            // result in sm_s / sm_have, which every warp has just read to decide `hot`: the barrier keeps a warp that
+            // is still waiting for its gathers from reading the NEW value and taking the other branch (found in
+            // round 2: rows went wrong once other kernels ran beside this one, profiles/r2_multistream_rejected.txt)
+            __syncthreads();
             if (w == first) {
               float sq = s;
               bool hq = have;

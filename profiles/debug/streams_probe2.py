@@ -11,7 +11,7 @@ else:
     from oracle import ref
     n, s, d, _ = ref.rmat_edges(20, 16, seed=1)
     indeg = np.bincount(d - 1, minlength=n)
-    for iters in (1, 2, 3):
+    for iters in (2, 3, 10):
         f = "/tmp/pr_i%d.npy" % iters
         subprocess.check_call(["timeout", "100", sys.executable, __file__, f, str(iters)], env=dict(os.environ, GM_AUX_STREAMS="2"))
         a = np.load(f)
