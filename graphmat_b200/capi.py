@@ -138,7 +138,7 @@ SYMBOLS = [
     "gm_push_sort", "gm_graph_set_edge_values", "gm_graph_exchange_x_parts", "gm_abi_struct_sizes",
     "gm_graph_exchange_buffer", "gm_graph_enable_peers", "gm_graph_peers_enabled", "gm_graph_peer_barrier",
     "gm_graph_push_x", "gm_vectors_need_alt", "gm_graph_slice_begin", "gm_graph_set_vertexproperties_slice",
-    "gm_graph_get_vertexproperties_slice", "gm_vectors_aux", "gm_graph_set_active_array", "gm_graph_edges_changed",
+    "gm_graph_get_vertexproperties_slice", "gm_vectors_aux", "gm_graph_set_active_array", "gm_graph_edges_changed", "gm_graph_detach_host",
 ]
 
 
@@ -247,6 +247,8 @@ class Graph:
 
     def __del__(self):
         try:
+            if self.h:  # garbage collection, not an orderly close(): never wait for the other ranks here
+                lib().gm_graph_detach_host(self.h)
             self.close()
         except Exception:
             pass

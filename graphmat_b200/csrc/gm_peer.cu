@@ -162,6 +162,8 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
   out->peer[g->rank] = out->local;
   if (g->world == 1) return 0;
   if (!g->host_gather) {
+    cudaFree(out->local);
+    *out = gm_sym();
     gm_set_error("peer memory: gm_graph_enable_peers was not called");
     return 1;
   }
@@ -179,6 +181,8 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
   }
   std::vector<peer_blob> all(g->world);
   if (g->host_gather(g->host_ctx, &mine, all.data(), (int)sizeof(peer_blob))) {
+    cudaFree(out->local);
+    *out = gm_sym();
     gm_set_error("peer memory: the host all-gather callback failed");
     return 1;
   }
@@ -260,6 +264,14 @@ extern "C" int gm_graph_enable_peers(gm_graph* g, gm_allgather_host_fn allgather
   return 0;
 }
 extern "C" int gm_graph_peers_enabled(const gm_graph* g) { return g->peers_on ? 1 : 0; }
+// Destroying symmetric buffers is collective (nobody frees what another process still has mapped).  A process that is
+// going down alone (an exception, interpreter shutdown) calls this first: its frees then skip the rendezvous instead of
+// waiting for ranks that will never come.
+extern "C" int gm_graph_detach_host(gm_graph* g) {
+  g->host_gather = nullptr;
+  g->host_ctx = nullptr;
+  return 0;
+}
 
 extern "C" int gm_graph_peer_barrier(gm_graph* g, int or_changed_flag) {
   if (g->world == 1) return 0;

@@ -205,6 +205,7 @@ int gm_graph_exchange_buffer(gm_graph* g, void* buf, long long bytes_per_rank); 
 typedef int (*gm_allgather_host_fn)(void* ctx, const void* mine, void* all, int bytes_per_rank);
 int gm_graph_enable_peers(gm_graph* g, gm_allgather_host_fn allgather_host, void* ctx);
 int gm_graph_peers_enabled(const gm_graph* g);
+int gm_graph_detach_host(gm_graph* g);  /* this process is going down alone: later destroys skip the collective rendezvous */
 int gm_graph_peer_barrier(gm_graph* g, int or_changed_flag); /* enqueue the barrier kernel on the graph's stream;
                                                             or_changed_flag: d_flags[0] becomes its OR over ranks */
 int gm_graph_push_x(gm_graph* g, gm_vectors* v, int dense); /* store this rank's slice of x (bit words + values,
