@@ -413,6 +413,8 @@ class Vectors:
 
     def __del__(self):
         try:
+            if self.h and self.graph is not None and self.graph.h:  # garbage collection: see Graph.__del__
+                lib().gm_graph_detach_host(self.graph.h)
             self.close()
         except Exception:
             pass
