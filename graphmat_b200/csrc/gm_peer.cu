@@ -55,7 +55,7 @@ struct ptr_table {
 // flags[q] = rank q's array of 2 * GM_MAX_WORLD words; word [parity * GM_MAX_WORLD + r] is written by rank r.
 // A rank cannot enter round k + 2 before everybody has left round k + 1, i.e. has read round k: two
 // alternating sets of words are enough.
-__global__ void k_peer_barrier(ptr_table flags, int rank, int world, unsigned round, int* changed, int* err) {
+__global__ void k_peer_barrier(const __grid_constant__ ptr_table flags, int rank, int world, unsigned round, int* changed, int* err) {
   __shared__ int any;
   if (threadIdx.x == 0) any = 0;
   __syncthreads();
@@ -90,7 +90,7 @@ __global__ void k_peer_barrier(ptr_table flags, int rank, int world, unsigned ro
 // W: unsigned (messages that are a multiple of 4 bytes) or unsigned char (e.g. TopSort's bool)
 template <class W>
 __global__ void __launch_bounds__(256)
-    k_push_x(ptr_table val, ptr_table bits, int n_peers, const W* __restrict__ lval,
+    k_push_x(const __grid_constant__ ptr_table val, const __grid_constant__ ptr_table bits, int n_peers, const W* __restrict__ lval,
              const unsigned* __restrict__ lbits, long long word_off, int bit_off, int n_pad, int wp, int dense) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)n_pad * wp;
@@ -116,7 +116,7 @@ __host__ __device__ inline int to_native0(int pub1, int n, int npart) {
 }
 
 // owned vertex properties -> the staging area of the rank whose public slice holds the vertex
-__global__ void k_permute_out_slices(const unsigned* vp, ptr_table staging, int n, int npart, const int* xidx, int n_pad,
+__global__ void k_permute_out_slices(const unsigned* vp, const __grid_constant__ ptr_table staging, int n, int npart, const int* xidx, int n_pad,
                                      int rank, int words_per, long long per) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long pub = t / words_per;
