@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(256) k_apply(prog_bytes<P> pb, int n_valid, in
 // A warp loads 32 words of the active set (y bits); only the non-empty words are visited, lane j taking bit j, so
 // a step touches 32 consecutive vertices exactly like the per-vertex kernels do, but a sparse frontier costs a few
 // hundred blocks instead of one thread per vertex (BFS on RMAT-22: 13 us -> ~3 us per sweep).
+constexpr int GM_WORD_SPARSE = 4;  // words with at most this many bits are walked by their own lane
 template <class P, class T, class V>
 __global__ void __launch_bounds__(256) k_send_words(prog_bytes<P> pb, int n_words, const V* __restrict__ vp,
                                                     const unsigned* __restrict__ active, T* __restrict__ x,
@@ -339,7 +340,24 @@ __global__ void __launch_bounds__(256) k_send_words(prog_bytes<P> pb, int n_word
   const int w = w0 + lane;
   unsigned word = w < n_words ? active[w] : 0u;
   unsigned out = word;
-  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  const int pc = __popc(word);
+  // a word with a few bits (the usual case on a thin frontier: about one active vertex per word) is walked by its own
+  // lane -- 32 words in flight per warp instead of 32 one-lane steps; dense words go through the whole warp, lane j = bit j
+  if (pc > 0 && pc <= GM_WORD_SPARSE) {
+    unsigned m = word;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int i = w * 32 + b;
+      T t;
+      (void)prog.P::send_message(vp[i], t);
+      bool on = true;
+      if constexpr (has_null_message<P, T>::value) on = !P::gm_null_message(t);
+      if (on) x[i] = t;
+      else out &= ~(1u << b);
+    }
+  }
+  unsigned lanes = __ballot_sync(0xffffffffu, pc > GM_WORD_SPARSE);
   while (lanes) {
     const int src = __ffs(lanes) - 1;
     lanes &= lanes - 1;
@@ -377,23 +395,33 @@ __global__ void __launch_bounds__(256) k_apply_words(prog_bytes<P> pb, int n_wor
   const unsigned word = w < n_words ? __ldg(ybits + w) : 0u;
   unsigned out = 0u;
   unsigned long long ents = 0;
-  unsigned lanes = __ballot_sync(0xffffffffu, word != 0);
+  auto one = [&](int i) -> bool {  // the apply loop body for vertex i (GraphMatRuntime.h:201-213); returns "changed"
+    V cur = vp[i];
+    const V old = cur;
+    const U msg = y[i];
+    prog.P::apply(msg, cur);
+    const bool changed = (old != cur);
+    vp[i] = cur;
+    if constexpr (RESET) reinterpret_cast<unsigned*>(y)[i] = 0xffffffffu;
+    if (changed && c_ptr) ents += (unsigned long long)(__ldg(c_ptr + x_off + i + 1) - __ldg(c_ptr + x_off + i));
+    return changed;
+  };
+  const int pc = __popc(word);
+  if (pc > 0 && pc <= GM_WORD_SPARSE) {  // few messages in this word: its own lane walks them (see k_send_words)
+    unsigned m = word;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (one(w * 32 + b)) out |= 1u << b;
+    }
+  }
+  unsigned lanes = __ballot_sync(0xffffffffu, pc > GM_WORD_SPARSE);
   while (lanes) {
     const int src = __ffs(lanes) - 1;
     lanes &= lanes - 1;
     const unsigned m = __shfl_sync(0xffffffffu, word, src);
     bool changed = false;
-    if ((m >> lane) & 1u) {
-      const int i = (w0 + src) * 32 + lane;
-      V cur = vp[i];
-      const V old = cur;
-      const U msg = y[i];
-      prog.P::apply(msg, cur);
-      changed = (old != cur);
-      vp[i] = cur;
-      if constexpr (RESET) reinterpret_cast<unsigned*>(y)[i] = 0xffffffffu;
-      if (changed && c_ptr) ents += (unsigned long long)(__ldg(c_ptr + x_off + i + 1) - __ldg(c_ptr + x_off + i));
-    }
+    if ((m >> lane) & 1u) changed = one((w0 + src) * 32 + lane);
     const unsigned cm = __ballot_sync(0xffffffffu, changed);
     if (lane == src) out = cm;
   }
