@@ -1,0 +1,69 @@
+"""Inputs and option sets for the graph_converter parity test (reference: src/graph_converter.cpp:162-338).
+Shared by tests/test_graph_converter.py and tests/golden/make_converter_golden.py."""
+import numpy as np
+
+N_VERTICES = 300
+
+
+def edges(seed=7, n=N_VERTICES, nnz=5000):
+    """Random edges with self loops and duplicates.  A duplicate carries the same weight as its twin
+    (weight = f(src, dst) = f(dst, src)): which twin survives --duplicatededges 0 is unspecified in the reference
+    (unstable parallel sort), so the fixtures do not depend on it."""
+    r = np.random.default_rng(seed)
+    src = r.integers(1, n + 1, nnz)
+    dst = r.integers(1, n + 1, nnz)
+    dst[::97] = src[::97]                      # self loops
+    k = len(src[1::53])                        # duplicates of the first k edges
+    src[1::53], dst[1::53] = src[:k].copy(), dst[:k].copy()
+    src[-1], dst[-1] = n, n - 1                # the largest id occurs
+    return src.astype(np.int64), dst.astype(np.int64)
+
+
+def weight(src, dst, kind):
+    w = ((src + dst) * 31 + src * dst * 17) % 97 + 1  # symmetric: (u, v) and (v, u) tie after --bidirectional too
+    if kind == "int":
+        return w
+    return w / 8.0 + 0.1                       # fractional: exercises %.8f / %.15lf
+
+
+def write_text(path, src, dst, w=None, header=True, n=N_VERTICES, kind="int"):
+    with open(path, "w") as f:
+        if header:
+            f.write("%d %d %d\n" % (n, n, len(src)))
+        for i in range(len(src)):
+            if w is None:
+                f.write("%d %d\n" % (src[i], dst[i]))
+            elif kind == "int":
+                f.write("%d %d %d\n" % (src[i], dst[i], w[i]))
+            else:
+                f.write("%d %d %.6f\n" % (src[i], dst[i], w[i]))
+
+
+# name -> (input kind, input has header, input has weights, converter arguments)
+CASES = {
+    "default_to_binary": ("int", True, True, []),
+    "identity_text": ("int", True, True, ["--outputformat", "1", "--selfloops", "1", "--duplicatededges", "1"]),
+    "dedupe_text": ("int", True, True, ["--outputformat", "1"]),
+    "keep_selfloops": ("int", True, True, ["--outputformat", "1", "--selfloops", "1"]),
+    "bidirectional": ("int", True, True, ["--outputformat", "1", "--bidirectional"]),
+    "uppertriangular": ("int", True, True, ["--outputformat", "1", "--uppertriangular"]),
+    "randomize_ids": ("int", True, True, ["--outputformat", "1", "--randomizeID"]),
+    "random_weights": ("int", True, True, ["--outputformat", "1", "--outputedgeweights", "3", "--r", "64",
+                                           "--duplicatededges", "1"]),
+    "double_weights": ("real", True, True, ["--outputformat", "1", "--edgeweighttype", "1"]),
+    "float_weights": ("real", True, True, ["--outputformat", "1", "--edgeweighttype", "2"]),
+    "float_to_binary": ("real", True, True, ["--edgeweighttype", "2", "--bidirectional"]),
+    "no_header_in": ("int", False, True, ["--outputformat", "1", "--inputheader", "0", "--nvertices", "320"]),
+    "no_header_in_max": ("int", False, True, ["--outputformat", "1", "--inputheader", "0"]),
+    "no_header_out": ("int", True, True, ["--outputformat", "1", "--outputheader", "0"]),
+    "no_weights": ("int", True, False, ["--outputformat", "1", "--inputedgeweights", "0", "--outputedgeweights", "0"]),
+    "unit_weights": ("int", True, False, ["--outputformat", "1", "--inputedgeweights", "0", "--outputedgeweights", "2"]),
+    "drop_weights_binary": ("int", True, True, ["--outputedgeweights", "0", "--uppertriangular"]),
+}
+
+
+def write_input(prefix, name):
+    kind, header, weights, _ = CASES[name]
+    src, dst = edges()
+    w = weight(src, dst, kind) if weights else None
+    write_text(prefix + "0", src, dst, w, header=header, kind=kind)
