@@ -214,13 +214,14 @@ int gm_sym_alloc(gm_graph* g, size_t bytes, gm_sym* out) {
   // agree on the outcome: a rank that could not map a peer must not leave the others storing into it
   std::vector<int> oks(g->world, 0);
   int ok = bad ? 0 : 1;
-  if (g->host_gather(g->host_ctx, &ok, oks.data(), (int)sizeof(int))) return 1;
+  const bool gathered = g->host_gather(g->host_ctx, &ok, oks.data(), (int)sizeof(int)) == 0;
+  if (!gathered) why = "the host all-gather callback failed";
   for (int q = 0; q < g->world; q++)
-    if (!oks[q]) bad = 1;
+    if (!gathered || !oks[q]) bad = 1;
   if (bad) {
     for (int q = 0; q < g->world; q++)
       if (out->opened[q]) cudaIpcCloseMemHandle(out->peer[q]);
-    host_barrier(g);
+    if (gathered) host_barrier(g);  // the importers have closed before anybody frees
     cudaFree(out->local);
     *out = gm_sym();
     gm_set_error("peer memory: a peer buffer could not be mapped (" + (why.empty() ? std::string("another rank failed") : why) + ")");
