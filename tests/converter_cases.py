@@ -67,3 +67,16 @@ def write_input(prefix, name):
     src, dst = edges()
     w = weight(src, dst, kind) if weights else None
     write_text(prefix + "0", src, dst, w, header=header, kind=kind)
+
+
+def write_helper_input(prefix):
+    """small edge list with empty columns (odd ids never occur as a destination) for tests/host/edgelist_check.cpp"""
+    r = np.random.default_rng(5)
+    n, nnz = 40, 160
+    src = r.integers(1, n + 1, nnz)
+    dst = r.integers(1, n // 2 + 1, nnz) * 2
+    write_text(prefix + "0", src, dst, weight(src, dst, "int"), n=n)
+
+
+def result_lines(stdout):
+    return "".join(line + "\n" for line in stdout.splitlines() if line.startswith("|"))

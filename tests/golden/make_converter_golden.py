@@ -1,6 +1,7 @@
 """Writes tests/golden/converter.json: sha256 and size of what the UNMODIFIED reference's graph_converter
 (oracle/_ref/graph_converter, built by `make -C oracle ref` from /root/reference/src/graph_converter.cpp)
-writes for every case of tests/converter_cases.py, plus the binary->text round trip.
+writes for every case of tests/converter_cases.py, plus the binary->text round trip; and
+tests/golden/edgelist_check.txt: what the reference's edge-list helpers return (oracle/_ref/edgelist_check).
 Run in the build container:  python tests/golden/make_converter_golden.py"""
 import hashlib
 import json
@@ -37,6 +38,13 @@ def main():
         convert(REF, ["--inputformat", "0", "--outputformat", "1", "--selfloops", "1", "--duplicatededges", "1"],
                 os.path.join(d, "default_to_binary.out"), os.path.join(d, "roundtrip"))
         gold["binary_to_text"] = digest(os.path.join(d, "roundtrip0"))
+        # the helpers graph_converter does not reach, through tests/host/edgelist_check.cpp built against the reference
+        cc.write_helper_input(os.path.join(d, "helpers"))
+        out = subprocess.run([os.path.join(os.path.dirname(REF), "edgelist_check"), os.path.join(d, "helpers")],
+                             capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        with open(os.path.join(HERE, "edgelist_check.txt"), "w") as f:
+            f.write(cc.result_lines(out.stdout))
     with open(os.path.join(HERE, "converter.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("wrote", len(gold), "digests")

@@ -108,6 +108,24 @@ def test_converter_rejects_bad_options(tmp_path):
     assert out.returncode != 0 and "4-byte edge values" in out.stdout
 
 
+def test_edgelist_helpers_match_reference(tmp_path):
+    """remove_empty_columns, filter_edges_by_row, get_dimensions, filter_edges, randomize_edge_direction and
+    ReadEdges(randomize) of GraphMat/edgelist.h: the same driver (tests/host/edgelist_check.cpp) built against the
+    product's header and against the reference's prints the same results."""
+    exe = os.path.join(ROOT, "apps", "bin", "edgelist_check")
+    if not os.path.exists(exe):
+        pytest.fail("apps/bin/edgelist_check is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    src = str(tmp_path / "helpers")
+    cc.write_helper_input(src)
+    mine = subprocess.run([exe, src], capture_output=True, text=True, timeout=60)
+    assert mine.returncode == 0, mine.stderr
+    assert cc.result_lines(mine.stdout) == open(os.path.join(util.GOLDEN, "edgelist_check.txt")).read()
+    ref = os.path.join(ROOT, "oracle", "_ref", "edgelist_check")
+    if os.path.exists(ref):
+        live = subprocess.run([ref, src], capture_output=True, text=True, timeout=60)
+        assert cc.result_lines(live.stdout) == cc.result_lines(mine.stdout)
+
+
 @pytest.mark.gpu
 def test_snapshot_format_round_trip(tmp_path):
     """Format 2 (this library's GraphMat-binary snapshot) -> text gives the same edge set as text -> text."""
