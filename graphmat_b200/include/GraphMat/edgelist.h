@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -64,6 +65,87 @@ bool read_text_edge(FILE* f, int* s, int* d, T* v, bool weights) {
   if (!weights) { *v = (T)1; return true; }
   return fscanf(f, text_fmt<T>::in(), v) == 1;
 }
+// grows the array to hold at least `need` edges (doubling; exact when the count is known up front)
+template <typename T>
+void reserve(edgelist_t<T>* el, size_t* cap, size_t need, bool exact = false) {
+  if (need <= *cap) return;
+  size_t c = exact ? need : std::max<size_t>(need, *cap ? *cap * 2 : 1024);
+  el->edges = reinterpret_cast<edge_t<T>*>(realloc(el->edges, c * sizeof(edge_t<T>)));
+  *cap = c;
+}
+
+// Binary records are (int src, int dst[, T val]) back to back.  With weights that is the memory layout of edge_t<T>
+// for 4- and 8-byte T, so the file is read straight into the array in one fread per file (the reference reads field
+// by field, edgelist.h:89-106: three library calls per edge, ~40 s for a billion edges); without weights the id pairs
+// are read in blocks and widened.  nnz < 0: no header, the record count comes from the file length and m, n from
+// the ids.  A header that promises more records than the file holds gets what is there.
+template <typename T>
+bool read_binary_records(FILE* fp, edgelist_t<T>* el, size_t* cap, long long nnz, bool weights, bool header, int* m, int* n) {
+  const size_t rec = 2 * sizeof(int) + (weights ? sizeof(T) : 0);
+  const long long here = ftello(fp);
+  if (here < 0 || fseeko(fp, 0, SEEK_END)) return false;
+  const long long in_file = (ftello(fp) - here) / (long long)rec;
+  if (fseeko(fp, here, SEEK_SET)) return false;
+  const long long want = nnz < 0 ? in_file : std::min(nnz, in_file);
+  if (want <= 0) return true;
+  if ((long long)el->nnz + want > 0x7fffffffLL) {
+    printf("graphmat_b200: more than 2^31-1 edges do not fit edgelist_t (int nnz, as in the reference)\n");
+    return false;
+  }
+  reserve(el, cap, (size_t)el->nnz + (size_t)want, true);
+  edge_t<T>* out = el->edges + el->nnz;
+  long long got = 0;
+  if (weights && sizeof(edge_t<T>) == rec) {
+    got = (long long)fread(out, rec, (size_t)want, fp);
+  } else {
+    const size_t block = 1 << 20;
+    unsigned char* buf = reinterpret_cast<unsigned char*>(malloc(block * rec));
+    while (got < want) {
+      const size_t k = fread(buf, rec, (size_t)std::min<long long>((long long)block, want - got), fp);
+      if (k == 0) break;
+      for (size_t i = 0; i < k; i++) {
+        const unsigned char* r = buf + i * rec;
+        edge_t<T>& e = out[got + (long long)i];
+        memcpy(&e.src, r, sizeof(int));
+        memcpy(&e.dst, r + sizeof(int), sizeof(int));
+        if (weights) memcpy(&e.val, r + 2 * sizeof(int), sizeof(T));
+        else e.val = (T)1;
+      }
+      got += (long long)k;
+    }
+    free(buf);
+  }
+  if (!header)
+    for (long long i = 0; i < got; i++) { *m = std::max(*m, out[i].src); *n = std::max(*n, out[i].dst); }
+  el->nnz += (int)got;
+  return true;
+}
+
+// the writing side of the same layouts
+template <typename T>
+void write_binary_records(FILE* fp, const edgelist_t<T>& el, bool weights) {
+  const size_t rec = 2 * sizeof(int) + (weights ? sizeof(T) : 0);
+  if (weights && sizeof(edge_t<T>) == rec) {
+    fwrite(el.edges, rec, (size_t)el.nnz, fp);
+    return;
+  }
+  const size_t block = 1 << 20;
+  unsigned char* buf = reinterpret_cast<unsigned char*>(malloc(block * rec));
+  for (size_t done = 0; done < (size_t)el.nnz;) {
+    const size_t k = std::min(block, (size_t)el.nnz - done);
+    for (size_t i = 0; i < k; i++) {
+      const edge_t<T>& e = el.edges[done + i];
+      unsigned char* r = buf + i * rec;
+      memcpy(r, &e.src, sizeof(int));
+      memcpy(r + sizeof(int), &e.dst, sizeof(int));
+      if (weights) memcpy(r + 2 * sizeof(int), &e.val, sizeof(T));
+    }
+    fwrite(buf, rec, k, fp);
+    done += k;
+  }
+  free(buf);
+}
+
 template <typename T>
 void write_text_edge(FILE* f, int s, int d, const T& v, bool weights) {
   fprintf(f, "%d %d", s, d);
@@ -98,26 +180,19 @@ void load_edgelist(const char* dir, edgelist_t<T>* edgelist, bool binaryformat =
         if (fscanf(fp, "%d %d %d", &m, &n, &nnz) != 3) { fclose(fp); break; }
       }
     }
-    int s, d;
-    T v;
-    long long got = 0;
-    while (nnz < 0 || got < nnz) {
-      bool ok;
-      if (binaryformat) {
-        ok = fread(&s, sizeof(int), 1, fp) == 1 && fread(&d, sizeof(int), 1, fp) == 1;
-        if (ok && edgeweights) ok = fread(&v, sizeof(T), 1, fp) == 1;
-        if (ok && !edgeweights) v = (T)1;
-      } else {
-        ok = detail::read_text_edge<T>(fp, &s, &d, &v, edgeweights);
+    if (binaryformat) {
+      if (!detail::read_binary_records<T>(fp, edgelist, &cap, nnz, edgeweights, header, &m, &n)) { fclose(fp); break; }
+    } else {
+      int s, d;
+      T v;
+      long long got = 0;
+      while (nnz < 0 || got < nnz) {
+        if (!detail::read_text_edge<T>(fp, &s, &d, &v, edgeweights)) break;
+        detail::reserve(edgelist, &cap, (size_t)edgelist->nnz + 1);
+        edgelist->edges[edgelist->nnz++] = edge_t<T>(s, d, v);
+        if (!header) { m = std::max(m, s); n = std::max(n, d); }
+        got++;
       }
-      if (!ok) break;
-      if ((size_t)edgelist->nnz == cap) {
-        cap = cap ? cap * 2 : 1024;
-        edgelist->edges = reinterpret_cast<edge_t<T>*>(realloc(edgelist->edges, cap * sizeof(edge_t<T>)));
-      }
-      edgelist->edges[edgelist->nnz++] = edge_t<T>(s, d, v);
-      if (!header) { m = std::max(m, s); n = std::max(n, d); }
-      got++;
     }
     edgelist->m = std::max(edgelist->m, m);
     edgelist->n = std::max(edgelist->n, n);
@@ -139,13 +214,11 @@ void write_edgelist(const char* dir, const edgelist_t<T>& edgelist, bool binaryf
     if (binaryformat) { int h[3] = {edgelist.m, edgelist.n, edgelist.nnz}; fwrite(h, sizeof(int), 3, fp); }
     else fprintf(fp, "%d %d %d\n", edgelist.m, edgelist.n, edgelist.nnz);
   }
-  for (int i = 0; i < edgelist.nnz; i++) {
-    const edge_t<T>& e = edgelist.edges[i];
-    if (binaryformat) {
-      fwrite(&e.src, sizeof(int), 1, fp);
-      fwrite(&e.dst, sizeof(int), 1, fp);
-      if (edgeweights) fwrite(&e.val, sizeof(T), 1, fp);
-    } else {
+  if (binaryformat) {
+    detail::write_binary_records<T>(fp, edgelist, edgeweights);
+  } else {
+    for (int i = 0; i < edgelist.nnz; i++) {
+      const edge_t<T>& e = edgelist.edges[i];
       detail::write_text_edge<T>(fp, e.src, e.dst, e.val, edgeweights);
     }
   }

@@ -62,11 +62,56 @@ CASES = {
 }
 
 
+# binary mtx inputs: name -> (input kind, header, weights, number of input files, converter arguments)
+BIN_CASES = {
+    "bin_in": ("int", True, True, 1, ["--inputformat", "0", "--outputformat", "1"]),
+    "bin_in_two_files": ("int", True, True, 2, ["--inputformat", "0", "--outputformat", "1"]),
+    "bin_in_no_weights": ("int", True, False, 1, ["--inputformat", "0", "--outputformat", "1", "--inputedgeweights", "0",
+                                                  "--outputedgeweights", "0"]),
+    "bin_in_no_header": ("int", False, True, 1, ["--inputformat", "0", "--outputformat", "1", "--inputheader", "0"]),
+    "bin_in_no_header_no_weights": ("int", False, False, 1, ["--inputformat", "0", "--outputformat", "0", "--inputheader", "0",
+                                                             "--inputedgeweights", "0", "--outputedgeweights", "0",
+                                                             "--outputheader", "0"]),
+    "bin_in_double": ("real", True, True, 1, ["--inputformat", "0", "--outputformat", "1", "--edgeweighttype", "1"]),
+    "bin_in_float": ("real", True, True, 1, ["--inputformat", "0", "--outputformat", "1", "--edgeweighttype", "2"]),
+    "bin_out_double": ("real", True, True, 1, ["--inputformat", "0", "--edgeweighttype", "1", "--bidirectional"]),
+}
+ALL_CASES = sorted(CASES) + sorted(BIN_CASES)
+
+
+def case_args(name):
+    return CASES[name][3] if name in CASES else BIN_CASES[name][4]
+
+
+def write_binary(path, src, dst, w=None, header=True, n=N_VERTICES, wtype=np.uint32):
+    """edgelist.h:208-240 of the reference: int m, n, nnz, then (int src, int dst[, T val]) records"""
+    with open(path, "wb") as f:
+        if header:
+            f.write(np.array([n, n, len(src)], np.int32).tobytes())
+        if w is None:
+            f.write(np.stack([src, dst], 1).astype(np.int32).tobytes())
+        else:
+            rec = np.zeros(len(src), dtype=[("s", np.int32), ("d", np.int32), ("v", wtype)])
+            rec["s"], rec["d"], rec["v"] = src, dst, w
+            f.write(rec.tobytes())
+
+
 def write_input(prefix, name):
-    kind, header, weights, _ = CASES[name]
     src, dst = edges()
+    if name in CASES:
+        kind, header, weights, _ = CASES[name]
+        w = weight(src, dst, kind) if weights else None
+        write_text(prefix + "0", src, dst, w, header=header, kind=kind)
+        return
+    kind, header, weights, nfiles, args = BIN_CASES[name]
+    wtype = np.uint32
+    if "--edgeweighttype" in args:
+        wtype = {"1": np.float64, "2": np.float32}[args[args.index("--edgeweighttype") + 1]]
     w = weight(src, dst, kind) if weights else None
-    write_text(prefix + "0", src, dst, w, header=header, kind=kind)
+    cut = np.linspace(0, len(src), nfiles + 1).astype(int)
+    for k in range(nfiles):                    # one rank reads <prefix>0, <prefix>1, ... (edgelist.h:250-253)
+        lo, hi = cut[k], cut[k + 1]
+        write_binary(prefix + str(k), src[lo:hi], dst[lo:hi], None if w is None else w[lo:hi], header=header, wtype=wtype)
 
 
 def write_helper_input(prefix):

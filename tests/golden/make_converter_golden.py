@@ -30,7 +30,8 @@ def convert(exe, args, src, dst):
 def main():
     gold = {}
     with tempfile.TemporaryDirectory() as d:
-        for name, (_, _, _, args) in cc.CASES.items():
+        for name in cc.ALL_CASES:
+            args = cc.case_args(name)
             cc.write_input(os.path.join(d, name + ".in"), name)
             convert(REF, args, os.path.join(d, name + ".in"), os.path.join(d, name + ".out"))
             gold[name] = digest(os.path.join(d, name + ".out0"))
