@@ -1321,11 +1321,11 @@ extern "C" int gm_vectors_create(gm_vectors** out, const gm_graph* g, int sizeof
   v->n_pad = g->n_pad;
   const size_t xb = (size_t)g->n_full * sizeof_T, bb = (size_t)(g->n_full >> 5) * 4;
   if (g->peers_on) {  // the message buffers are mapped on every rank (gm_peer.cu); zero-filled by gm_sym_alloc
+    v->sym = true;  // before the allocations: a failure of the second one releases the first through gm_sym_free
     if (gm_sym_alloc(gm, xb, &v->s_val) || gm_sym_alloc(gm, bb, &v->s_bits)) {
       gm_vectors_destroy(v);
       return 1;
     }
-    v->sym = true;
     v->x_val = v->s_val.local;
     v->x_bits = (unsigned*)v->s_bits.local;
   } else {
